@@ -1,0 +1,165 @@
+"""Generate golden fixtures from the UNMODIFIED reference  --  TEST INFRASTRUCTURE ONLY.
+
+Runs in the build container only (needs /root/reference, which does not exist on the GPU box).
+Imports the reference read-only with the two out-of-tree shims of SURVEY.md section 8c:
+  1. a stub ``torchfile`` module (utils.py:6 imports it; used only by load_vgg16, dead at vgg_w=0);
+  2. ``Tensor.cuda(dev)`` / ``Module.cuda(dev)`` rebound to ``.to(dev)`` so ``cuda_device='cpu'`` works.
+Loads deterministic synthetic parameters (``council_oracle.synth_all_states``) into the reference's
+``Council_Trainer``, runs one training iteration (dis_update -> dis_council_update -> gen_update,
+train.py:241-250) and writes the observed values to ``tests/golden/<case>.json``.
+
+    python oracle/make_golden.py            # regenerates every case in CASES
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+import council_oracle as co  # noqa: E402
+
+REF = os.environ.get('COUNCIL_REF_DIR', '/root/reference')
+
+# case name -> (config yaml, overrides, image size, batch, iteration)
+CASES = {
+    # BASELINE.json configs[0]: glasses 128x128, council_size=2, batch=1, all gates open
+    'glasses128_n2_b1': ('glasses', {'council.council_size': 2}, 128, 1, 20001),
+    # same network before either gate opens (no council loss, no focus loss, no dis_council step)
+    'glasses64_n2_b2_early': ('glasses', {'council.council_size': 2}, 64, 2, 100),
+    # male2female hyper-parameters (K=4 with N=4 -> one duplicated peer; mask_tv_w=0) at a CPU-friendly size
+    'm2f64_n4_b2': ('male2female', {}, 64, 2, 60001),
+    # selfie2anime: b2a-only direction (gan_w asymmetry trainer_council.py:775-777), focus weights 0
+    'anime64_n3_b2': ('selfie2anime', {'council.council_size': 3}, 64, 2, 2001),
+}
+
+PROBE_PARAMS = {
+    'gen': ['enc_content.model.0.conv.weight', 'enc_content.model.3.model.2.model.1.conv.weight',
+            'dec.model.0.model.0.model.0.conv.weight', 'dec.model.2.conv.weight', 'dec.model.9.conv.weight',
+            'dec.model.9.conv.bias', 'mlp.model.2.fc.weight', 'mlp.model.0.fc.bias'],
+    'dis': ['cnns.0.0.conv.weight', 'cnns.1.3.conv.weight', 'cnns.0.4.weight', 'cnns.1.4.bias'],
+    'dis_council': ['cnns.0.0.conv.weight', 'cnns.0.4.weight', 'cnns.1.5.weight', 'cnns.1.2.conv.bias'],
+}
+
+
+def load_config(name, overrides):
+    hp = yaml.safe_load(open(os.path.join(ROOT, 'configs', name + '.yaml')))
+    for k, v in overrides.items():
+        d = hp
+        ks = k.split('.')
+        for kk in ks[:-1]:
+            d = d[kk]
+        d[ks[-1]] = v
+    return hp
+
+
+def probe(t, n=8):
+    """A few deterministic samples + moments of a tensor: enough to pin it, small enough to commit."""
+    f = t.detach().double().flatten()
+    idx = torch.linspace(0, f.numel() - 1, n).long()
+    return {'mean': f.mean().item(), 'absmean': f.abs().mean().item(), 'l2': f.norm().item(),
+            'samples': [f[i].item() for i in idx]}
+
+
+def import_reference():
+    sys.modules.setdefault('torchfile', types.ModuleType('torchfile'))
+    sys.path.insert(0, REF)
+    import torch.nn as nn
+    torch.Tensor.cuda = lambda self, device=None, *a, **k: self.to(device if device is not None else 'cpu')
+    nn.Module.cuda = lambda self, device=None: self.to(device if device is not None else 'cpu')
+    from trainer_council import Council_Trainer
+    return Council_Trainer
+
+
+def run_case(Council_Trainer, case):
+    cfg, overrides, size, batch, iteration = CASES[case]
+    hp = load_config(cfg, overrides)
+    hp['batch_size'] = batch
+    hp['iteration'] = iteration
+    torch.set_num_threads(8)
+    co.seed_all(hp['random_seed'])
+    trainer = Council_Trainer(hp, 'cpu')
+    states = co.synth_all_states(hp, seed=7)
+    for name, lst in states.items():
+        fam, d = name.rsplit('_', 1)
+        mods = getattr(trainer, '%s_%s_s' % (fam, d))
+        for i, sd in enumerate(lst):
+            mods[i].load_state_dict(sd)
+    x_a, x_b = co.synth_inputs(batch, size, seed=123)
+    co.seed_all(hp['random_seed'] + 1)
+    dirs = [d for d in ('a2b', 'b2a') if hp['do_' + d]]
+    N = hp['council']['council_size']
+    out = {'case': case, 'config': cfg, 'overrides': overrides, 'size': size, 'batch': batch,
+           'iteration': iteration, 'state_seed': 7, 'input_seed': 123, 'rng_seed': hp['random_seed'] + 1,
+           'torch': torch.__version__, 'reference': 'Onr/Council-GAN @ 7fe8f8a (unmodified, CPU, shims only)'}
+
+    trainer.dis_update(x_a, x_b, hp)
+    out['loss_dis_total'] = [float(v) for v in trainer.loss_dis_total_s]
+    ran = True
+    trainer.loss_dis_council_total_s = None
+    trainer.dis_council_update(x_a, x_b, hp)
+    ran = trainer.loss_dis_council_total_s is not None
+    out['dis_council_ran'] = ran
+    out['loss_dis_council_total'] = [float(v) for v in trainer.loss_dis_council_total_s] if ran else []
+    trainer.gen_update(x_a, x_b, hp, iteration)
+    out['loss_gen_total'] = [float(v) for v in trainer.loss_gen_total_s]
+    d0 = dirs[0]
+    adv = trainer.loss_gen_adv_a2b_s if d0 == 'a2b' else trainer.loss_gen_adv_b2a_s
+    out['loss_gen_adv'] = [float(v) for v in adv]
+    cl = trainer.council_loss_ab_s if d0 == 'a2b' else trainer.council_loss_ba_s
+    out['council_loss'] = [float(v) for v in cl]
+    z1 = trainer.loss_gen_mask_zero_one_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_zero_one_ba_s
+    out['loss_gen_mask_zero_one'] = [float(v) for v in z1]
+    mt = trainer.loss_gen_mask_total_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_total_ba_s
+    out['loss_gen_mask_total'] = [float(v) for v in mt]
+    tv = trainer.loss_gen_mask_TV_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_TV_ba_s
+    out['loss_gen_mask_TV'] = [float(v) for v in tv]
+    out['w_match'] = float(trainer.w_match_a2b_conf if d0 == 'a2b' else trainer.w_match_b2a_conf)
+    # post-iteration parameters (each family stepped exactly once) and the grads that produced them
+    post = {}
+    for fam in ('gen', 'dis', 'dis_council'):
+        mods = getattr(trainer, '%s_%s_s' % (fam, d0), None)
+        if mods is None or len(mods) == 0:
+            continue
+        for i in range(N):
+            sd = mods[i].state_dict()
+            named = dict(mods[i].named_parameters())
+            for key in PROBE_PARAMS[fam]:
+                rec = {'post': probe(sd[key])}
+                if fam == 'gen' and named[key].grad is not None:
+                    rec['grad'] = probe(named[key].grad)
+                post['%s.%d.%s' % (fam, i, key)] = rec
+    out['params'] = post
+    # a fresh forward of member 0 AFTER the iteration (pins the updated generator end to end)
+    with torch.no_grad():
+        g0 = getattr(trainer, 'gen_%s_s' % d0)[0]
+        src = x_a if d0 == 'a2b' else x_b
+        c, _ = g0.encode(src)
+        s = torch.randn(batch, hp['gen']['style_dim'], 1, 1, generator=torch.Generator().manual_seed(5))
+        xf, mask = g0.decode(c, s, src, return_mask=True)
+    out['post_x_fake0'] = probe(xf, 16)
+    out['post_mask0'] = probe(mask, 16)
+    return out
+
+
+def main():
+    Council_Trainer = import_reference()
+    os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
+    cases = sys.argv[1:] or list(CASES)
+    for case in cases:
+        out = run_case(Council_Trainer, case)
+        path = os.path.join(ROOT, 'tests', 'golden', case + '.json')
+        with open(path, 'w') as f:
+            json.dump(out, f, indent=1)
+        print(case, 'dis', out['loss_dis_total'], 'disc', out['loss_dis_council_total'], 'gen', out['loss_gen_total'])
+
+
+if __name__ == '__main__':
+    main()
