@@ -1,0 +1,78 @@
+// Shared helpers for libcouncil_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/council_b200.h"
+
+namespace cg {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+extern int g_tc_mode;
+
+inline int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+#define CG_REQUIRE(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            cg::set_error(__VA_ARGS__);      \
+            return CG_ERR_ARG;               \
+        }                                    \
+    } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == CG_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == CG_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if (act == CG_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+// geometry helpers shared by host code
+struct ConvDims {
+    int Hin, Win;   // size the convolution sees (after optional x2 upsample)
+    long Mpix;      // B*Ho*Wo
+    int Ktot;       // KH*KW*Cin
+};
+inline ConvDims conv_dims(const cg_conv_geom& g) {
+    ConvDims d;
+    d.Hin = g.ups ? 2 * g.H : g.H;
+    d.Win = g.ups ? 2 * g.W : g.W;
+    d.Mpix = (long)g.B * g.Ho * g.Wo;
+    d.Ktot = g.KH * g.KW * g.Cin;
+    return d;
+}
+int validate_geom(const cg_conv_geom& g);
+
+// ---- SIMT fp32 implicit-GEMM convolutions (conv_simt.cu) ----
+int simt_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y,
+                  int act, float slope, cudaStream_t st);
+// writes gradient w.r.t. the tensor the convolution SEES (upsampled size if g.ups)
+int simt_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float* dx_seen,
+                    const float* addend, const float* mask_src, float mask_slope, cudaStream_t st);
+int simt_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
+size_t simt_wgrad_ws(const cg_conv_geom& g);
+int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t colsum_ws(int G, long rows, int C);
+int pool2x2_sum(const float* d_up, float* dx, const float* addend, const float* mask_src, float mask_slope,
+                long N, int H, int W, int C, cudaStream_t st);
+
+// ---- tcgen05 TF32 implicit-GEMM convolutions (conv_tc.cu) ----
+bool tc_fwd_supported(const cg_conv_geom& g);
+int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y,
+                int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace cg

@@ -1,0 +1,306 @@
+"""ctypes binding of libcouncil_b200.so (the C ABI declared in include/council_b200.h).
+
+PyTorch is used here for device memory (``torch.empty``), the current CUDA stream and nothing else:
+every method hands raw device pointers to a hand-written sm_100a kernel.  There is NO fallback:
+if the shared library is missing or no CUDA device is present, constructing :class:`CudaOps` raises.
+
+Tensor conventions (see the header): fp32, channels-last activations stacked over the council
+``[G, B, H, W, C]``; weights stacked OHWI ``[G, Cout, KH, KW, Cin]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcouncil_b200.so')
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('G', 'x_groups', 'B', 'H', 'W', 'Cin', 'Ho', 'Wo', 'Cout',
+                                         'KH', 'KW', 'stride', 'pad', 'ups')]
+
+
+_fp = C.c_void_p
+_SIGS = {
+    'cg_last_error': (C.c_char_p, []),
+    'cg_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
+    'cg_set_tensor_core_mode': (C.c_int, [C.c_int]),
+    'cg_launch_count': (C.c_uint64, []),
+    'cg_conv_fwd': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_conv_dgrad': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_conv_wgrad': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    'cg_conv_workspace_bytes': (C.c_size_t, [C.POINTER(ConvGeom), C.c_int]),
+    'cg_in_stats': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_norm_act_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp]),
+    'cg_norm_act_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp, C.c_size_t, _fp]),
+    'cg_mask_head_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_mask_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_avgpool_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_avgpool_bwd': (C.c_int, [_fp, _fp] + [C.c_int] * 7 + [_fp]),
+    'cg_acc_slice': (C.c_int, [_fp, _fp, C.c_long, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_gather_images': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_nchw_to_nhwc': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_nhwc_to_nchw': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_lsgan_fwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_lsgan_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_focus_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_focus_bwd': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
+    'cg_adam_step': (C.c_int, [_fp, _fp, _fp, _fp, C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, _fp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the library and attach argtypes.  Works without a GPU (symbol check only)."""
+    if not os.path.exists(path):
+        raise RuntimeError('%s not found: build it with `python -m council_gan_b200.build` '
+                           '(there is no CPU or PyTorch fallback for this path)' % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv_out_size(h, k, stride, pad, ups):
+    return ((2 * h if ups else h) + 2 * pad - k) // stride + 1
+
+
+class CudaOps:
+    """The product op-set: every method is one (or a few) launches of our own kernels."""
+
+    name = 'cuda'
+    dtype = torch.float32
+
+    def __init__(self, device='cuda:0', workspace_bytes=256 << 20):
+        if not torch.cuda.is_available():
+            raise RuntimeError('council_gan_b200 needs a CUDA device (sm_100a); no CPU path exists')
+        self.lib = load_library()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        rc = self.lib.cg_device_info(C.byref(sm), C.byref(maj), C.byref(mnr))
+        if rc < 0:
+            raise RuntimeError('cg_device_info: ' + self.lib.cg_last_error().decode())
+        self.sm_count, self.cc = sm.value, (maj.value, mnr.value)
+        if self.cc[0] != 10:
+            raise RuntimeError('libcouncil_b200.so is built for sm_100a only; device is sm_%d%d' % self.cc)
+        self._ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError('%s failed (%d): %s' % (what, rc, self.lib.cg_last_error().decode()))
+
+    def _ws_for(self, nbytes):
+        if nbytes > self._ws.numel():
+            self._ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+
+    def launch_count(self):
+        return int(self.lib.cg_launch_count())
+
+    def set_tensor_core_mode(self, mode):
+        return self.lib.cg_set_tensor_core_mode(int(mode))
+
+    @staticmethod
+    def _chk(*ts):
+        for t in ts:
+            if t is not None:
+                assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda, 'need contiguous fp32 CUDA tensors'
+
+    # -- convolution ------------------------------------------------------------------------------
+    def _geom(self, xshape, w, stride, pad, ups):
+        Gx, B, H, W, Cin = xshape
+        G, Cout, KH, KW, Cin2 = w.shape
+        assert Cin == Cin2, (xshape, tuple(w.shape))
+        Ho, Wo = conv_out_size(H, KH, stride, pad, ups), conv_out_size(W, KW, stride, pad, ups)
+        return ConvGeom(G, Gx, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, int(bool(ups)))
+
+    def conv_fwd(self, x, w, bias, stride, pad, ups=False, act=ACT_NONE, slope=0.2):
+        self._chk(x, w, bias)
+        g = self._geom(x.shape, w, stride, pad, ups)
+        y = self.empty(g.G, g.B, g.Ho, g.Wo, g.Cout)
+        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 0))
+        self._ck(self.lib.cg_conv_fwd(C.byref(g), _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ws), ws.numel(),
+                                      self._stream()), 'cg_conv_fwd')
+        return y
+
+    def conv_dgrad(self, dy, w, x_shape, stride, pad, ups=False, addend=None, mask_src=None, mask_slope=0.0):
+        self._chk(dy, w, addend, mask_src)
+        G = w.shape[0]
+        g = self._geom((G,) + tuple(x_shape[1:]), w, stride, pad, ups)
+        assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout), (tuple(dy.shape), (g.G, g.B, g.Ho, g.Wo, g.Cout))
+        dx = self.empty(g.G, g.B, g.H, g.W, g.Cin)
+        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 1))
+        self._ck(self.lib.cg_conv_dgrad(C.byref(g), _p(dy), _p(w), _p(dx), _p(addend), _p(mask_src), mask_slope,
+                                        _p(ws), ws.numel(), self._stream()), 'cg_conv_dgrad')
+        return dx
+
+    def conv_wgrad(self, x, dy, dw, db, stride, pad, ups=False):
+        """dw [G,Cout,KH,KW,Cin] and db [G,Cout] (or None) are OUTPUT views (overwritten)."""
+        self._chk(x, dy, dw, db)
+        g = self._geom(x.shape, dw, stride, pad, ups)
+        assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout)
+        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 2))
+        self._ck(self.lib.cg_conv_wgrad(C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(),
+                                        self._stream()), 'cg_conv_wgrad')
+
+    # -- instance norm / AdaIN --------------------------------------------------------------------
+    def in_stats(self, y, eps=1e-5):
+        self._chk(y)
+        G, B, H, W, Cc = y.shape
+        mean, rstd = self.empty(G, B, Cc), self.empty(G, B, Cc)
+        ws = self._ws_for(((H * W + 511) // 512) * G * B * Cc * 8)
+        self._ck(self.lib.cg_in_stats(_p(y), _p(mean), _p(rstd), G, B, H * W, Cc, eps, _p(ws), ws.numel(),
+                                      self._stream()), 'cg_in_stats')
+        return mean, rstd
+
+    def norm_act_fwd(self, y, mean, rstd, adain=None, off=0, res=None, act=ACT_NONE, ups=False):
+        self._chk(y, mean, rstd, adain, res)
+        G, B, H, W, Cc = y.shape
+        z = self.empty(G, B, 2 * H if ups else H, 2 * W if ups else W, Cc)
+        P = adain.shape[-1] if adain is not None else 0
+        self._ck(self.lib.cg_norm_act_fwd(_p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(res), _p(z), G, B, H, W, Cc,
+                                          act, int(bool(ups)), self._stream()), 'cg_norm_act_fwd')
+        return z
+
+    def norm_act_bwd(self, dz, y, mean, rstd, adain=None, off=0, act=ACT_NONE, ups=False, d_adain=None):
+        self._chk(dz, y, mean, rstd, adain, d_adain)
+        G, B, H, W, Cc = y.shape
+        dy = self.empty(G, B, H, W, Cc)
+        P = adain.shape[-1] if adain is not None else 0
+        ws = self._ws_for((((H * W + 511) // 512) + 1) * G * B * Cc * 8)
+        self._ck(self.lib.cg_norm_act_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
+                                          G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
+                 'cg_norm_act_bwd')
+        return dy
+
+    # -- mask head --------------------------------------------------------------------------------
+    def mask_head_fwd(self, h, x_in):
+        self._chk(h, x_in)
+        G, B, H, W, _ = h.shape
+        x_fake, mask = self.empty(G, B, H, W, 4), self.empty(G, B, H, W, 4)
+        self._ck(self.lib.cg_mask_head_fwd(_p(h), _p(x_in), _p(x_fake), _p(mask), G, B, H * W, self._stream()),
+                 'cg_mask_head_fwd')
+        return x_fake, mask
+
+    def mask_head_bwd(self, h, x_in, d_xfake, d_mask=None):
+        self._chk(h, x_in, d_xfake, d_mask)
+        G, B, H, W, _ = h.shape
+        dh = self.empty(G, B, H, W, 12)
+        self._ck(self.lib.cg_mask_head_bwd(_p(h), _p(x_in), _p(d_xfake), _p(d_mask), _p(dh), G, B, H * W,
+                                           self._stream()), 'cg_mask_head_bwd')
+        return dh
+
+    # -- image-space helpers ----------------------------------------------------------------------
+    def avgpool_fwd(self, x):
+        self._chk(x)
+        G, B, H, W, Cc = x.shape
+        y = self.empty(G, B, H // 2, W // 2, Cc)
+        self._ck(self.lib.cg_avgpool_fwd(_p(x), _p(y), G * B, H, W, Cc, self._stream()), 'cg_avgpool_fwd')
+        return y
+
+    def avgpool_bwd(self, dy, dx, nch, accumulate):
+        self._chk(dy, dx)
+        G, B, H, W, Cx = dx.shape
+        self._ck(self.lib.cg_avgpool_bwd(_p(dy), _p(dx), G * B, H, W, dy.shape[-1], Cx, nch, int(bool(accumulate)),
+                                         self._stream()), 'cg_avgpool_bwd')
+
+    def acc_slice(self, dst, src, nch):
+        self._chk(dst, src)
+        npix = dst.numel() // dst.shape[-1]
+        assert npix == src.numel() // src.shape[-1]
+        self._ck(self.lib.cg_acc_slice(_p(dst), _p(src), npix, dst.shape[-1], src.shape[-1], nch, self._stream()),
+                 'cg_acc_slice')
+
+    def gather_images(self, pool, idx, x_in, G, Bt):
+        """pool [S,H,W,4]; idx int32 [G,Bt] slot table; x_in [1,B,H,W,4] or None -> [G,Bt,H,W,4|8]"""
+        self._chk(pool, x_in)
+        assert idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.numel() == G * Bt
+        S, H, W, _ = pool.shape
+        B = x_in.shape[1] if x_in is not None else 1
+        y = self.empty(G, Bt, H, W, 8 if x_in is not None else 4)
+        self._ck(self.lib.cg_gather_images(_p(pool), idx.data_ptr(), _p(x_in), _p(y), G, Bt, B, H * W, self._stream()),
+                 'cg_gather_images')
+        return y
+
+    def nchw_to_nhwc(self, x, Cp):
+        self._chk(x)
+        N, Cc, H, W = x.shape
+        y = self.empty(N, H, W, Cp)
+        self._ck(self.lib.cg_nchw_to_nhwc(_p(x), _p(y), N, Cc, H * W, Cp, self._stream()), 'cg_nchw_to_nhwc')
+        return y
+
+    def nhwc_to_nchw(self, x, Cc):
+        self._chk(x)
+        *lead, H, W, Cp = x.shape
+        N = 1
+        for d in lead:
+            N *= d
+        y = self.empty(*lead, Cc, H, W)
+        self._ck(self.lib.cg_nhwc_to_nchw(_p(x), _p(y), N, Cc, H * W, Cp, self._stream()), 'cg_nhwc_to_nchw')
+        return y
+
+    # -- losses -----------------------------------------------------------------------------------
+    def lsgan_fwd(self, out, targets, weights, nseg, loss, accumulate):
+        """out [G, nseg*B, h, w, 1]; targets/weights device [nseg]; returns sums [G,nseg] and updates
+        loss[G] (+)= sum_seg weights[seg] * mean_seg((out - target[seg])^2)."""
+        self._chk(out, targets, weights, loss)
+        G = out.shape[0]
+        n_per_seg = out[0].numel() // nseg
+        sums = self.empty(G, nseg)
+        self._ck(self.lib.cg_lsgan_fwd(_p(out), _p(targets), _p(weights), _p(sums), _p(loss), G, nseg, n_per_seg,
+                                       int(bool(accumulate)), self._stream()), 'cg_lsgan_fwd')
+        return sums
+
+    def lsgan_bwd(self, out, targets, coef, nseg):
+        self._chk(out, targets, coef)
+        G = out.shape[0]
+        n_per_seg = out[0].numel() // nseg
+        dout = torch.empty_like(out)
+        self._ck(self.lib.cg_lsgan_bwd(_p(out), _p(targets), _p(coef), _p(dout), G, nseg, n_per_seg, self._stream()),
+                 'cg_lsgan_bwd')
+        return dout
+
+    def focus_fwd(self, mask, center, eps):
+        self._chk(mask)
+        G, B, H, W, _ = mask.shape
+        sums = self.empty(G, 4)
+        ws = self._ws_for(((B * H * W + 2047) // 2048) * G * 16)
+        self._ck(self.lib.cg_focus_fwd(_p(mask), _p(sums), G, B, H, W, center, eps, _p(ws), ws.numel(), self._stream()),
+                 'cg_focus_fwd')
+        return sums
+
+    def focus_bwd(self, mask, coef, center, eps):
+        self._chk(mask, coef)
+        G, B, H, W, _ = mask.shape
+        dmask = torch.empty_like(mask)
+        self._ck(self.lib.cg_focus_bwd(_p(mask), _p(coef), _p(dmask), G, B, H, W, center, eps, self._stream()),
+                 'cg_focus_bwd')
+        return dmask
+
+    # -- optimiser --------------------------------------------------------------------------------
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+        self._chk(p, g, m, v)
+        self._ck(self.lib.cg_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                                       step, grad_scale, self._stream()), 'cg_adam_step')

@@ -1,0 +1,144 @@
+/*
+ * council_b200.h -- C ABI of libcouncil_b200.so: the sm_100a kernels behind the Council-GAN
+ * training step (dis_update / dis_council_update / gen_update).
+ *
+ * The reference (Onr/Council-GAN) has no FFI: every device op on this path is a PyTorch library
+ * call made from networks.py / trainer_council.py.  Each entry point below replaces one of those
+ * call sites (cited per function, paths relative to the reference tree) so that a maintainer can
+ * bind it with ctypes from the same Python code.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - all tensors are dense fp32; activations are channels-last, stacked over the council:
+ *         act[G][B][H][W][C]      G = council members in the launch ("groups"), C % 4 == 0
+ *     a source with `x_groups == 1` is shared (broadcast) by all G members;
+ *   - convolution weights are stacked OHWI:  w[G][Cout][KH][KW][Cin]   (reference: OIHW per member);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates,
+ *     and returns 0 on success or a negative cg_status; cg_last_error() describes the last failure
+ *     of the calling thread;
+ *   - `ws` / `ws_bytes` is caller-provided scratch; if it is too small the call fails with
+ *     CG_ERR_WORKSPACE and cg_last_error() reports the size needed.
+ */
+#ifndef COUNCIL_B200_H
+#define COUNCIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CG_OK = 0,
+    CG_ERR_ARG = -1,        /* unsupported shape / argument */
+    CG_ERR_WORKSPACE = -2,  /* workspace too small */
+    CG_ERR_CUDA = -3,       /* CUDA runtime / driver error */
+    CG_ERR_NO_DEVICE = -4   /* no sm_100 device */
+} cg_status;
+
+/* activation codes (Conv2dBlock activations, networks.py:494-507) */
+enum { CG_ACT_NONE = 0, CG_ACT_RELU = 1, CG_ACT_LRELU = 2, CG_ACT_TANH = 3 };
+
+/* Geometry of one grouped convolution.  Spatial sizes are those of the STORED input tensor;
+ * with `ups` the convolution sees nearest-upsample-x2 of it (nn.Upsample(scale_factor=2),
+ * networks.py:385, folded into the gather).  Ho/Wo are the output sizes. */
+typedef struct {
+    int32_t G, x_groups;         /* groups in w / y; groups in x (1 = shared input) */
+    int32_t B, H, W, Cin;        /* stored input  [x_groups][B][H][W][Cin]  */
+    int32_t Ho, Wo, Cout;        /* output        [G][B][Ho][Wo][Cout]      */
+    int32_t KH, KW, stride, pad; /* zero padding (nn.ZeroPad2d, networks.py:473-474) */
+    int32_t ups;                 /* 0/1 */
+} cg_conv_geom;
+
+const char* cg_last_error(void);
+/* Library / device introspection: returns the SM count of the current device (>0) or a cg_status. */
+int cg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* 0 = SIMT fp32 reference kernels only, 1 = tcgen05 TF32 tensor-core path where a layer qualifies.
+ * Returns the previous value.  Default 1. */
+int cg_set_tensor_core_mode(int mode);
+/* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
+uint64_t cg_launch_count(void);
+
+/* ---- convolution (Conv2dBlock conv + bias + activation, networks.py:513-520; nn.Linear with
+ *      H=W=KH=KW=1, networks.py:531,563) ------------------------------------------------------- */
+/* y = act(conv(x, w) + bias).  bias may be NULL. */
+int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w, const float* bias, float* y,
+                int act, float slope, void* ws, size_t ws_bytes, void* stream);
+/* dx = (conv_transpose(dy, w) [+ addend]) * act'(mask_src)      (autograd of the call above)
+ * dx has the STORED input shape; with g->ups the 2x2 upsample fan-in is summed.
+ * addend / mask_src (same shape as dx) may be NULL; act' = mask_src > 0 ? 1 : mask_slope. */
+int cg_conv_dgrad(const cg_conv_geom* g, const float* dy, const float* w, float* dx,
+                  const float* addend, const float* mask_src, float mask_slope,
+                  void* ws, size_t ws_bytes, void* stream);
+/* dw[G][Cout][KH][KW][Cin] = sum over pixels dy (x) im2col(x);  db[G][Cout] = sum dy (NULL: skip).
+ * Deterministic (fixed split-K order). */
+int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float* dy, float* dw, float* db,
+                  void* ws, size_t ws_bytes, void* stream);
+size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
+
+/* ---- instance norm / AdaIN (nn.InstanceNorm2d networks.py:483; AdaptiveInstanceNorm2d :640-653) */
+/* mean, rstd [G][B][C] over H*W (biased variance, rstd = 1/sqrt(var+eps)). */
+int cg_in_stats(const float* y, float* mean, float* rstd, int G, int B, int HW, int C, float eps,
+                void* ws, size_t ws_bytes, void* stream);
+/* z = act(gamma * (y-mean)*rstd + beta) [+ res];  AdaIN parameters come straight from the MLP
+ * output adain[G][B][P]: beta = adain[.., off : off+C], gamma = adain[.., off+C : off+2C]
+ * (assign_adain_params, networks.py:303-312).  adain == NULL: plain instance norm.
+ * ups: z is written nearest-upsampled x2 ([G][B][2H][2W][C]).  res (shape of y) may be NULL. */
+int cg_norm_act_fwd(const float* y, const float* mean, const float* rstd, const float* adain, int P,
+                    int off, const float* res, float* z, int G, int B, int H, int W, int C, int act,
+                    int ups, void* stream);
+/* backward of the above w.r.t. y and the AdaIN parameters (d_adain[..][off:off+2C] is overwritten).
+ * dz has the shape of z (upsampled if ups).  The residual branch gradient is dz itself. */
+int cg_norm_act_bwd(const float* dz, const float* y, const float* mean, const float* rstd,
+                    const float* adain, int P, int off, float* dy, float* d_adain, int G, int B,
+                    int H, int W, int C, int act, int ups, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- attention-mask head (Decoder_V2_atten.forward networks.py:398-407) ----------------------- */
+/* h[G][B][HW][12] = tanh output of dec.model.9; x_in[B][HW][4] (shared); outputs padded to 4 ch. */
+int cg_mask_head_fwd(const float* h, const float* x_in, float* x_fake, float* mask, int G, int B,
+                     int HW, void* stream);
+/* dh_pre[G][B][HW][12] = gradient w.r.t. the PRE-tanh output of dec.model.9. d_mask may be NULL. */
+int cg_mask_head_bwd(const float* h, const float* x_in, const float* d_xfake, const float* d_mask,
+                     float* dh_pre, int G, int B, int HW, void* stream);
+
+/* ---- image-space helpers ---------------------------------------------------------------------- */
+/* nn.AvgPool2d(3, 2, padding=1, count_include_pad=False), networks.py:32,129 */
+int cg_avgpool_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+/* dx[N][H][W][Cx] (first nch lanes) = or += avgpool^T(dy[N][H/2][W/2][Cy] first nch lanes) */
+int cg_avgpool_bwd(const float* dy, float* dx, int N, int H, int W, int Cy, int Cx, int nch,
+                   int accumulate, void* stream);
+/* dst[n][..][0:nch] += src[n][..][0:nch]  (pixel counts equal) */
+int cg_acc_slice(float* dst, const float* src, long npix, int Cd, int Cs, int nch, void* stream);
+/* y[g][n] = pool[idx[g*Bt+n]] (4 lanes) ++ x_in[n % B] (4 lanes, if x_in != NULL -> 8-lane output):
+ * builds discriminator minibatches (fake ++ real; torch.cat((x, x_input),1) networks.py:152). */
+int cg_gather_images(const float* pool, const int32_t* idx, const float* x_in, float* y, int G,
+                     int Bt, int B, int HW, void* stream);
+/* NCHW [N][C][HW] <-> channels-last [N][HW][Cp] (Cp >= C, pad lanes zeroed) */
+int cg_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, void* stream);
+int cg_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int Cp, void* stream);
+
+/* ---- losses ----------------------------------------------------------------------------------- */
+/* LSGAN (networks.py:64,90,166,194).  out[G][nseg][n_per_seg]; sums[G][nseg] = sum (out-target[seg])^2;
+ * loss[g] (+)= sum_seg weights[seg] * mean_seg((out-target[seg])^2).  targets/weights: device [nseg]. */
+int cg_lsgan_fwd(const float* out, const float* targets, const float* weights, float* sums, float* loss,
+                 int G, int nseg, int n_per_seg, int accumulate, void* stream);
+/* dout = coef[g][seg] * (out - target[seg])   (coef device pointer, [G][nseg]) */
+int cg_lsgan_bwd(const float* out, const float* targets, const float* coef, float* dout, int G,
+                 int nseg, int n_per_seg, void* stream);
+/* focus-loss sums over a mask [G][B][H][W][4] (3 live lanes), trainer_council.py:230-250:
+ * sums[G][4] = { sum 1/(|m-c|+eps), sum m, sum |m[h+1]-m[h]|, sum |m[w+1]-m[w]| } */
+int cg_focus_fwd(const float* mask, float* sums, int G, int B, int H, int W, float center, float eps,
+                 void* ws, size_t ws_bytes, void* stream);
+/* dmask = coef[g][0]*d(zero_one term) + coef[g][1]*d(sum m) + coef[g][2]*d(TV sums) */
+int cg_focus_bwd(const float* mask, const float* coef, float* dmask, int G, int B, int H, int W,
+                 float center, float eps, void* stream);
+
+/* ---- optimiser (torch.optim.Adam as used at trainer_council.py:170-179) ----------------------- */
+int cg_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COUNCIL_B200_H */
