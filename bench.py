@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- training images/sec of the Council-GAN step (dis_update + dis_council_update + gen_update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full training iteration (train.py:241-250 order) over one synthetic minibatch.
+Default workload = BASELINE.json configs[1]: male2female 256x256, council_size=4, batch 8 per GPU
+(weak scaling: configs[3] is the same at 8 GPUs, global batch 64).  All gates open (iteration 60001).
+
+Prints ONE JSON line (rank 0).  `value` = images/sec with inputs resident in HBM; `e2e` = the same through
+the public Council_Trainer API with HOST (pinned) image tensors: H2D copies and the D2H loss read are inside
+the timed region.  `roofline` is for the dominant convolution kernel, timed live with CUDA events on the
+launching stream.  `cpu_baseline` / `--impl reference` time the CPU oracle port (oracle/council_oracle.py, a
+restatement of the reference validated against it) on the host cores on a bounded sample (batch 1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+WORKLOADS = {
+    # name: (config yaml, council_size, per-GPU batch, image size, iteration with every gate open)
+    'male2female_256_n4_b8': ('male2female', 4, 8, 256, 60001),
+    'selfie2anime_256_n4_b4': ('selfie2anime', 4, 4, 256, 2001),
+    'glasses_128_n2_b1': ('glasses', 2, 1, 128, 20001),
+    'male2female_512_n6_b2': ('male2female', 6, 2, 512, 60001),
+    'tiny_64_n2_b2': ('glasses', 2, 2, 64, 20001),
+}
+ALG_GMAC_PER_IMAGE_MEMBER_256 = 486.7  # algorithmic work, K=4
+
+
+def load_hp(workload):
+    cfg, n, b, size, it = WORKLOADS[workload]
+    hp = yaml.safe_load(open(os.path.join(ROOT, 'configs', cfg + '.yaml')))
+    hp['council']['council_size'] = n
+    hp['batch_size'] = b
+    hp['iteration'] = it
+    for k in ('new_size', 'crop_image_height', 'crop_image_width'):
+        hp[k] = size
+    return hp, n, b, size, it
+
+
+def synth(batch, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, 3, size, size, generator=g) * 2 - 1, torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_oracle_rate(workload, steps, warmup):
+    """images/sec of the CPU oracle port on a bounded sample (batch 1) of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import council_oracle as co
+    hp, n, b, size, it = load_hp(workload)
+    hp['batch_size'] = 1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    states = co.synth_all_states(hp, seed=7)
+    tr = co.OracleTrainer(hp, states)
+    co.seed_all(1)
+    x_a, x_b = synth(1, size, 123)
+
+    def step():
+        tr.dis_update(x_a, x_b, hp)
+        tr.dis_council_update(x_a, x_b, hp)
+        tr.gen_update(x_a, x_b, hp, it)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='male2female_256_n4_b8', choices=list(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tc', type=int, default=1, help='0: SIMT fp32 kernels only, 1: tcgen05 TF32 where supported')
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    hp, n_members, batch, size, it = load_hp(args.workload)
+    scale = (size / 256.0) ** 2
+    metric, unit = 'training images/sec (gen+dis step)', 'images/s'
+    config = {'workload': args.workload, 'council_size': n_members, 'batch_per_gpu': batch, 'global_batch': batch * world,
+              'image': '%dx%d' % (size, size), 'parallelism': 'dp%d' % world, 'iteration': it,
+              'l2': 'per-step working set (saved activations, several GB) >> 126 MB L2; no explicit flush'}
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle port
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        rate, dt, cores = cpu_oracle_rate(args.workload, args.steps, args.warmup)
+        line = {'impl': 'reference', 'metric': metric, 'value': rate, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': rate, 'unit': unit, 'cores': cores, 'kind': 'port',
+                                 'sample': 'one full iteration (dis+dis_council+gen) at batch 1 of the same config; '
+                                           'oracle/council_oracle.py (torch CPU fp32), validated against the reference'},
+                'e2e': {'value': rate, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = 'cuda:%d' % local_rank
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    from council_gan_b200 import Council_Trainer
+    import random
+    import numpy as np
+    random.seed(1)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    trainer = Council_Trainer(hp, dev)
+    ops = trainer.ops
+    ops.set_tensor_core_mode(args.tc)
+    xa_h, xb_h = synth(batch * world, size, 123)
+    xa_h = xa_h[rank * batch:(rank + 1) * batch].contiguous().pin_memory()
+    xb_h = xb_h[rank * batch:(rank + 1) * batch].contiguous().pin_memory()
+    xa_d, xb_d = xa_h.to(dev), xb_h.to(dev)
+
+    def step(xa, xb):
+        trainer.dis_update(xa, xb, hp)
+        trainer.dis_council_update(xa, xb, hp)
+        trainer.gen_update(xa, xb, hp, it)
+        trainer.update_learning_rate()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 0)):
+        step(xa_d, xb_d)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.start_timing()
+    l0 = ops.launch_count()
+    ms = timed(lambda: step(xa_d, xb_d), args.steps)
+    launches = ops.launch_count() - l0
+    ktimes = ops.stop_timing()
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    value = batch * world / (ms_per_step * 1e-3)
+
+    # end to end through the public API with host tensors (H2D inside, loss read back)
+    d2h = [0]
+
+    def e2e_step():
+        step(xa_h, xb_h)
+        vals = [float(v) for v in trainer.loss_gen_total_s] + [float(v) for v in trainer.loss_dis_total_s]
+        d2h[0] = 4 * len(vals) + 4 * 6 * n_members
+        return vals
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e = {'value': batch * world / (ms_e2e * 1e-3), 'unit': unit, 'ms_per_step': ms_e2e,
+           'h2d_bytes_per_step': int(2 * xa_h.numel() * 4), 'd2h_bytes_per_step': int(d2h[0])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # roofline of the dominant kernel (largest share of the timed region among the timed conv launches)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    roofline = None
+    if ktimes:
+        key, (tot_ms, cnt, flops) = max(ktimes.items(), key=lambda kv: kv[1][0])
+        tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2.0  # TF32 runs at half the bf16 tensor rate
+        ach = flops / (tot_ms / cnt * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': key, 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
+                    'traffic': None, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
+                    'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 operands)' if peaks else 'fallback 1400/2')}
+    alg_tflop = 2 * ALG_GMAC_PER_IMAGE_MEMBER_256 * 1e9 * scale * n_members * batch * world / 1e12
+    line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32' if args.tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
+            'gpu_launches': int(launches), 'roofline': roofline,
+            'step_algorithmic_tflops': alg_tflop / (ms_per_step * 1e-3) / world,
+            'losses': {'gen': [float(v) for v in trainer.loss_gen_total_s], 'dis': [float(v) for v in trainer.loss_dis_total_s]}}
+    if not args.no_cpu_baseline:
+        rate, dt, cores = cpu_oracle_rate(args.workload, 1, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': unit, 'cores': cores, 'kind': 'port',
+                                'sample': 'one full iteration at batch 1 of the same config after one warm-up '
+                                          '(oracle/council_oracle.py, torch CPU fp32, %d threads)' % cores}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -63,7 +63,10 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     if (!g) return 0;
     ConvDims d = conv_dims(*g);
     size_t need = 0;
-    if (which == 1 && g->ups) need = (size_t)g->G * g->B * d.Hin * d.Win * g->Cin * sizeof(float);
+    if (which == 1) {
+        if (g->ups) need = (size_t)g->G * g->B * d.Hin * d.Win * g->Cin * sizeof(float);
+        if (g_tc_mode && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }
+    }
     if (which == 2) {
         size_t a = simt_wgrad_ws(*g), b = colsum_ws(g->G, d.Mpix, g->Cout);
         need = a > b ? a : b;
@@ -83,6 +86,7 @@ extern "C" int cg_conv_dgrad(const cg_conv_geom* g, const float* dy, const float
                              const float* mask_src, float mask_slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_tc_mode && tc_dgrad_supported(*g)) return tc_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, ws, ws_bytes, st);
     if (!g->ups) return simt_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, st);
     size_t need = cg_conv_workspace_bytes(g, 1);
     if (need > ws_bytes) {
@@ -103,4 +107,9 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
         return colsum(dy, db, g->G, d.Mpix, g->Cout, ws, ws_bytes, st);
     }
     return CG_OK;
+}
+
+extern "C" int cg_upsample2x_bwd(const float* d_up, float* dx, int N, int H, int W, int C, void* stream) {
+    CG_REQUIRE(C % 4 == 0, "upsample2x_bwd: C=%d must be a multiple of 4", C);
+    return pool2x2_sum(d_up, dx, nullptr, nullptr, 0.f, N, H, W, C, (cudaStream_t)stream);
 }

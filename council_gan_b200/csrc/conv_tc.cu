@@ -1,9 +1,568 @@
-// tcgen05 TF32 implicit-GEMM convolution (placeholder until the tensor-core kernel lands).
+// tcgen05 TF32 implicit-GEMM convolution for sm_100a.
+//
+//   D[128 pixels x BN couts] (fp32, TMEM) += A[128 x 32] (im2col tile of x, smem) * B[BN x 32] (weights, smem)
+//
+// * A tiles are gathered by TMA in IM2COL mode straight from the channels-last activation tensor
+//   [G*B][H][W][Cin]: the zero padding of nn.ZeroPad2d (networks.py:473-474) is the TMA out-of-bound
+//   fill, the stride is the TMA traversal stride -- there is no pad kernel and no im2col buffer.
+// * B tiles are 2-D TMA boxes of the OHWI weight matrix [G*Cout][KH*KW*Cin] (K-major).
+// * both land in shared memory in the 128-byte swizzled K-major layout tcgen05.mma reads; operands are
+//   fp32 in HBM, converted to TF32 by the tensor map data type; accumulation is fp32 in tensor memory.
+// * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+//   allocator), warps 2..5 = epilogue (tcgen05.ld -> bias / activation / addend / mask -> global).
+//   smem ring of STAGES (A,B) tiles with full/empty mbarriers; two TMEM accumulator stages so the epilogue
+//   of tile i overlaps the mainloop of tile i+1.
+// * all N council members are one launch: the member index is folded into the tensor-map coordinates
+//   (image index g*B+n for A, row g*Cout+co for B), i.e. a grouped GEMM over the council.
+//
+// The same kernel serves the data gradient: the host passes dy as the activation, a transposed /
+// flipped copy of the weights, and (for stride-2 layers) one launch "class" per output parity with its
+// own im2col bounding box and a strided output mapping (see tc_conv_dgrad).
+//
+// Reference call sites replaced: nn.Conv2d forward (networks.py:513,516) and cuDNN dgrad via autograd.
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
 namespace cg {
-bool tc_fwd_supported(const cg_conv_geom&) { return false; }
-int tc_conv_fwd(const cg_conv_geom&, const float*, const float*, const float*, float*, int, float, void*, size_t, cudaStream_t) {
-    set_error("tensor-core path not built");
-    return CG_ERR_ARG;
+
+// ------------------------------------------------------------------------------------------------
+// driver entry points for tensor-map encoding (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_sm_count = 0;
+static int g_driver_version = 0;
+static std::once_flag g_once;
+
+static void init_driver() {
+    std::call_once(g_once, [] {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_encode_tiled = (EncodeTiledFn)fn;
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_encode_im2col = (EncodeIm2colFn)fn;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDriverGetVersion(&g_driver_version);
+    });
 }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;            // leading byte offset (ignored for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row core-matrix groups
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;          // pixels per tile (TMEM lanes)
+constexpr int TC_BK = 32;           // fp32 channels per stage = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;     // 6 warps
+constexpr int TC_MAX_CLASSES = 4;   // stride-2 dgrad: one im2col map per output parity class
+
+struct TcClass {
+    CUtensorMap amap;     // im2col map of the activation for this class
+    int w0, h0;           // base coordinate of output pixel (0,0): lower corner
+    int out_h0, out_w0;   // output pixel (p,q) is written to (p*out_sh + out_h0, q*out_sw + out_w0)
+    int wrow_off;         // row offset into the weight matrix for this class
+    int pad_;
+};
+struct TcParams {
+    CUtensorMap bmap;               // weights [rows][Ktot_class] 2-D
+    TcClass cls[TC_MAX_CLASSES];
+    int ncls;
+    int G, xg_images;               // groups; images per group in the activation map (0: shared input)
+    int B, P, Q;                    // output grid per class: P x Q pixels per image
+    int Cin, Cout, KH, KW, stride;  // KH,KW: taps per class
+    int bn;                         // N tile
+    int out_H, out_W, out_sh, out_sw;  // full output spatial size and class strides
+    int w_rows_per_group;           // weight rows per group (ncls * Cout for dgrad classes)
+    float* y; const float* bias; const float* addend; const float* mask_src;
+    int act; float slope;
+    int stages;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_bytes = TC_BM * TC_BK * 4;
+    const int b_bytes = p.bn * TC_BK * 4;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int MT = (p.B * p.P * p.Q + TC_BM - 1) / TC_BM;  // pixel tiles per (group, class)
+    const int NT = p.Cout / p.bn;
+    const int tiles = p.G * p.ncls * NT * MT;
+    const int kchunks = p.Cin / TC_BK;
+    const int kiters = p.KH * p.KW * kchunks;
+    const int tmem_cols = 2 * p.bn < 32 ? 32 : 2 * p.bn;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.bmap);
+        for (int c = 0; c < p.ncls; c++) prefetch_tmap(&p.cls[c].amap);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; s++) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int a = 0; a < 2; a++) {
+                mbar_init(&tfull_bar[a], 1);
+                mbar_init(&tempty_bar[a], 128);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        // TMEM allocation (power of two >= 32 columns), whole warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int mt = t % MT;
+                int r = t / MT;
+                int nt = r % NT;
+                r /= NT;
+                int c = r % p.ncls;
+                int g = r / p.ncls;
+                const TcClass& cl = p.cls[c];
+                long m0 = (long)mt * TC_BM;
+                int img = (int)(m0 / (p.P * p.Q));
+                int rem = (int)(m0 - (long)img * p.P * p.Q);
+                int pp = rem / p.Q, qq = rem - pp * p.Q;
+                int n_coord = g * p.xg_images + img;
+                int w_coord = cl.w0 + qq * p.stride;
+                int h_coord = cl.h0 + pp * p.stride;
+                int wrow = g * p.w_rows_per_group + cl.wrow_off + nt * p.bn;
+                for (int kh = 0; kh < p.KH; kh++)
+                    for (int kw = 0; kw < p.KW; kw++)
+                        for (int kc = 0; kc < kchunks; kc++) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                            uint8_t* sb = sa + a_bytes;
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                            tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa, kc * TC_BK, w_coord, h_coord, n_coord,
+                                               (uint16_t)kw, (uint16_t)kh);
+                            tma_load_2d(&p.bmap, &full_bar[stage], sb, ((kh * p.KW + kw) * kchunks + kc) * TC_BK, wrow);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(p.bn);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+                for (int k = 0; k < kiters; k++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    uint32_t sb = sa + a_bytes;
+                    uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    uint64_t bdesc = make_kmajor_sw128_desc(sb);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; kk++) {
+                        // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzled row: +2 in the 16-byte address field
+                        umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const long PQ = (long)p.P * p.Q;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            int mt = t % MT;
+            int r = t / MT;
+            int nt = r % NT;
+            r /= NT;
+            int c = r % p.ncls;
+            int g = r / p.ncls;
+            const TcClass& cl = p.cls[c];
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            long m = (long)mt * TC_BM + row;
+            bool valid = m < (long)p.B * PQ;
+            long out_off = 0;
+            if (valid) {
+                int img = (int)(m / PQ);
+                int rem = (int)(m - (long)img * PQ);
+                int pp = rem / p.Q, qq = rem - pp * p.Q;
+                long pix = ((long)(g * p.B + img) * p.out_H + (pp * p.out_sh + cl.out_h0)) * p.out_W + (qq * p.out_sw + cl.out_w0);
+                out_off = pix * p.Cout + nt * p.bn;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                if (valid) {
+                    if (p.bias) {
+                        const float* bp = p.bias + (long)g * p.Cout + nt * p.bn + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] += __ldg(bp + j);
+                    }
+                    if (p.addend) {
+                        const float4* ap = reinterpret_cast<const float4*>(p.addend + out_off + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 a = __ldg(ap + j);
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        }
+                    }
+                    if (p.mask_src) {
+                        const float4* mp = reinterpret_cast<const float4*>(p.mask_src + out_off + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 a = __ldg(mp + j);
+                            v[4 * j] *= a.x > 0.f ? 1.f : p.slope; v[4 * j + 1] *= a.y > 0.f ? 1.f : p.slope;
+                            v[4 * j + 2] *= a.z > 0.f ? 1.f : p.slope; v[4 * j + 3] *= a.w > 0.f ? 1.f : p.slope;
+                        }
+                    } else if (p.act != CG_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = apply_act(v[j], p.act, p.slope);
+                    }
+                    float4* yp = reinterpret_cast<float4*>(p.y + out_off + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long ktot, int bn) {
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)w, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights rows=%ld ktot=%ld bn=%d) failed: %d", rows, ktot, bn, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+// activation [N][H][W][C] viewed by TMA as (C, W, H, N); bounding box corners as in CUTLASS
+// (cutlass/conv/collective/detail.hpp compute_lower/upper_corner_whd): lower = -pad_lo, upper = pad_hi - (K-1).
+static int encode_act_map(CUtensorMap* map, const float* x, long N, int H, int W, int C, int lo_w, int lo_h, int up_w, int up_h,
+                          int stride) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    int lower[2] = {lo_w, lo_h};
+    int upper[2] = {up_w, up_h};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, TC_BK, TC_BM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col(N=%ld H=%d W=%d C=%d corners %d,%d / %d,%d stride %d) failed: %d", N, H, W, C, lo_w, lo_h,
+                  up_w, up_h, stride, (int)r);
+        return CG_ERR_CUDA;
+    }
+    // driver <= 13.1: small tensors need bit 21 of the second descriptor word cleared (same workaround as CUTLASS
+    // cute/atom/copy_traits_sm90_im2col.hpp:477-483)
+    if (g_driver_version <= 13010 && (long)N * H * W * C * 4 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    return CG_OK;
+}
+
+static int pick_bn(int cout) {
+    if (cout % 256 == 0) return 256;
+    if (cout == 128) return 128;
+    if (cout == 64) return 64;
+    return 0;
+}
+
+bool tc_fwd_supported(const cg_conv_geom& g) {
+    init_driver();
+    if (!g_encode_tiled || !g_encode_im2col) return false;
+    if (g.ups) return false;
+    if (g.Cin % TC_BK != 0) return false;
+    if (pick_bn(g.Cout) == 0) return false;
+    if (g.pad > 120 || g.KH > 120) return false;
+    if ((long)g.B * g.Ho * g.Wo < TC_BM) return false;  // tiny maps: the SIMT kernel is fine
+    return true;
+}
+
+static int launch_tc(TcParams& p, cudaStream_t st) {
+    int a_bytes = TC_BM * TC_BK * 4, b_bytes = p.bn * TC_BK * 4;
+    int stage_bytes = a_bytes + b_bytes;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
+            return CG_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    int MT = cdiv((long)p.B * p.P * p.Q, TC_BM);
+    long tiles = (long)p.G * p.ncls * (p.Cout / p.bn) * MT;
+    int grid = (int)(tiles < g_sm_count ? tiles : g_sm_count);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+    return check_launch("conv_tc_kernel");
+}
+
+int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, int act, float slope, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+    init_driver();
+    TcParams p{};
+    p.bn = pick_bn(g.Cout);
+    long ktot = (long)g.KH * g.KW * g.Cin;
+    if (int rc = encode_weights_map(&p.bmap, w, (long)g.G * g.Cout, ktot, p.bn)) return rc;
+    long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
+    if (int rc = encode_act_map(&p.cls[0].amap, x, nimg, g.H, g.W, g.Cin, -g.pad, -g.pad, g.pad - (g.KW - 1), g.pad - (g.KH - 1), g.stride))
+        return rc;
+    p.cls[0].w0 = -g.pad; p.cls[0].h0 = -g.pad; p.cls[0].out_h0 = 0; p.cls[0].out_w0 = 0; p.cls[0].wrow_off = 0;
+    p.ncls = 1;
+    p.G = g.G; p.xg_images = g.x_groups == 1 ? 0 : g.B;
+    p.B = g.B; p.P = g.Ho; p.Q = g.Wo;
+    p.Cin = g.Cin; p.Cout = g.Cout; p.KH = g.KH; p.KW = g.KW; p.stride = g.stride;
+    p.out_H = g.Ho; p.out_W = g.Wo; p.out_sh = 1; p.out_sw = 1;
+    p.w_rows_per_group = g.Cout;
+    p.y = y; p.bias = bias; p.addend = nullptr; p.mask_src = nullptr; p.act = act; p.slope = slope;
+    return launch_tc(p, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// data gradient on the same kernel
+//
+// dx[ih] = sum_kh dy[(ih + pad - kh)/s] * w[kh]  over the kh with (ih + pad - kh) % s == 0.
+// For the input-parity class ph = (ih + pad) % s only kh = ph + s*t, t < T = K/s, contribute, and with
+// ih = ihf + s*i the sum is a T-tap stride-1 convolution over dy:
+//     dx[ihf + s*i] = sum_r dy[i - padl + r] * w[ph + s*(T-1-r)],   padl = (T-1) - (ihf + pad - ph)/s
+// so each class is a forward convolution of dy with transposed+flipped weights wt[g][class][ci][r][s][co],
+// an im2col box with lower corner -padl, and an output written with stride s at offset ihf.
+// ------------------------------------------------------------------------------------------------
+__global__ void dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, long total, int Cout, int Cin, int KH,
+                                              int KW, int s) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int TH = KH / s, TW = KW / s;
+    int co = (int)(i % Cout);
+    long t = i / Cout;
+    int ss = (int)(t % TW); t /= TW;
+    int r = (int)(t % TH); t /= TH;
+    int ci = (int)(t % Cin); t /= Cin;
+    int cls = (int)(t % (s * s));
+    int g = (int)(t / (s * s));
+    int ph = cls / s, pw = cls - ph * s;
+    int kh = ph + s * (TH - 1 - r), kw = pw + s * (TW - 1 - ss);
+    wt[i] = __ldg(w + ((((long)g * Cout + co) * KH + kh) * KW + kw) * Cin + ci);
+}
+
+bool tc_dgrad_supported(const cg_conv_geom& g) {
+    init_driver();
+    if (!g_encode_tiled || !g_encode_im2col) return false;
+    int s = g.stride;
+    if (s > 2 || g.KH % s || g.KW % s) return false;
+    if (g.Cout % TC_BK != 0) return false;      // K dimension of the dgrad GEMM
+    if (pick_bn(g.Cin) == 0) return false;      // N dimension
+    int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
+    if (Hin % s || Win % s) return false;
+    if ((long)g.B * (Hin / s) * (Win / s) < TC_BM) return false;
+    return true;
+}
+
+size_t tc_dgrad_ws(const cg_conv_geom& g) {
+    size_t wt = (size_t)g.G * g.Cout * g.KH * g.KW * g.Cin * sizeof(float);
+    wt = (wt + 1023) & ~(size_t)1023;
+    size_t up = g.ups ? (size_t)g.G * g.B * 4 * g.H * g.W * g.Cin * sizeof(float) : 0;
+    return wt + up;
+}
+
+int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float* dx, const float* addend, const float* mask_src,
+                  float mask_slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+    init_driver();
+    size_t need = tc_dgrad_ws(g);
+    if (need > ws_bytes) {
+        set_error("conv_dgrad(tc): workspace %zu < %zu bytes", ws_bytes, need);
+        return CG_ERR_WORKSPACE;
+    }
+    const int s = g.stride, TH = g.KH / s, TW = g.KW / s, ncls = s * s;
+    const int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
+    float* wt = (float*)ws;
+    size_t wt_bytes = ((size_t)g.G * g.Cout * g.KH * g.KW * g.Cin * sizeof(float) + 1023) & ~(size_t)1023;
+    float* d_seen = g.ups ? (float*)((uint8_t*)ws + wt_bytes) : dx;
+    long total = (long)g.G * g.Cout * g.KH * g.KW * g.Cin;
+    dgrad_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wt, total, g.Cout, g.Cin, g.KH, g.KW, s);
+    if (int rc = check_launch("dgrad_weight_transform")) return rc;
+
+    TcParams p{};
+    p.bn = pick_bn(g.Cin);
+    long ktot = (long)TH * TW * g.Cout;
+    if (int rc = encode_weights_map(&p.bmap, wt, (long)g.G * ncls * g.Cin, ktot, p.bn)) return rc;
+    for (int c = 0; c < ncls; c++) {
+        int ph = c / s, pw = c - ph * s;
+        int ihf = ((ph - g.pad) % s + s) % s, iwf = ((pw - g.pad) % s + s) % s;
+        int padl_h = (TH - 1) - (ihf + g.pad - ph) / s, padl_w = (TW - 1) - (iwf + g.pad - pw) / s;
+        int Hc = Hin / s, Wc = Win / s;
+        int up_h = Hc - g.Ho - padl_h, up_w = Wc - g.Wo - padl_w;
+        if (int rc = encode_act_map(&p.cls[c].amap, dy, (long)g.G * g.B, g.Ho, g.Wo, g.Cout, -padl_w, -padl_h, up_w, up_h, 1)) return rc;
+        p.cls[c].w0 = -padl_w; p.cls[c].h0 = -padl_h;
+        p.cls[c].out_h0 = ihf; p.cls[c].out_w0 = iwf;
+        p.cls[c].wrow_off = c * g.Cin;
+    }
+    p.ncls = ncls;
+    p.G = g.G; p.xg_images = g.B;
+    p.B = g.B; p.P = Hin / s; p.Q = Win / s;
+    p.Cin = g.Cout; p.Cout = g.Cin; p.KH = TH; p.KW = TW; p.stride = 1;
+    p.out_H = Hin; p.out_W = Win; p.out_sh = s; p.out_sw = s;
+    p.w_rows_per_group = ncls * g.Cin;
+    p.y = d_seen; p.bias = nullptr;
+    p.addend = g.ups ? nullptr : addend; p.mask_src = g.ups ? nullptr : mask_src;
+    p.act = CG_ACT_NONE; p.slope = mask_slope;
+    if (int rc = launch_tc(p, st)) return rc;
+    if (g.ups) return pool2x2_sum(d_seen, dx, addend, mask_src, mask_slope, (long)g.G * g.B, g.H, g.W, g.Cin, st);
+    return CG_OK;
+}
+
 }  // namespace cg

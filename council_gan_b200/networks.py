@@ -320,28 +320,31 @@ class CouncilGen(_StackedNet):
             w, b = w[sl:sl + 1], b[sl:sl + 1]
         return w, b
 
-    def _conv_norm(self, x, s, sl, adain, act, res, ups, saved):
-        """conv(+bias) -> IN/AdaIN statistics -> normalise(+gamma/beta) -> activation (+residual)."""
+    def _conv_norm(self, x, s, sl, adain, act, res, ups_out, saved):
+        """conv(+bias) -> IN/AdaIN statistics -> normalise(+gamma/beta) -> activation (+residual).
+        ups_out: the normalise pass writes its result nearest-upsampled x2 (nn.Upsample, networks.py:385), so
+        the following convolution is a plain 3x3 on the materialised tensor (TMA im2col cannot halve indices)."""
         ops = self.ops
         w, b = self._w(s, sl)
-        y = ops.conv_fwd(x, w, b, s.stride, s.pad, ups=ups)
+        y = ops.conv_fwd(x, w, b, s.stride, s.pad)
         mean, rstd = ops.in_stats(y)
         off = self.adain_off.get(s.key, 0)
-        z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, False)
+        z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
         if saved is not None:
             saved.append((x, y, mean, rstd))
         return z
 
-    def _conv_norm_bwd(self, dz, s, rec, adain, d_adain, act, ups, addend, need_dx=True):
-        """Backward of _conv_norm: fills the weight gradient, returns d(input)."""
+    def _conv_norm_bwd(self, dz, s, rec, adain, d_adain, act, ups_out, addend, need_dx=True):
+        """Backward of _conv_norm: fills the weight gradient, returns d(input).  With ups_out, dz has the
+        upsampled shape and the 2x2 fan-in is summed while it is read."""
         ops = self.ops
         x, y, mean, rstd = rec
         off = self.adain_off.get(s.key, 0)
-        dy = ops.norm_act_bwd(dz, y, mean, rstd, adain, off, act, False, d_adain)
-        ops.conv_wgrad(x, dy, self.bank.g(s.wname), None, s.stride, s.pad, ups=ups)
+        dy = ops.norm_act_bwd(dz, y, mean, rstd, adain, off, act, ups_out, d_adain)
+        ops.conv_wgrad(x, dy, self.bank.g(s.wname), None, s.stride, s.pad)
         if not need_dx:
             return None
-        return ops.conv_dgrad(dy, self.bank.p(s.wname), x.shape, s.stride, s.pad, ups=ups, addend=addend)
+        return ops.conv_dgrad(dy, self.bank.p(s.wname), x.shape, s.stride, s.pad, addend=addend)
 
     # -- forward ---------------------------------------------------------------------------------------
     def encode(self, x_img, saved=None, sl=None):
@@ -374,13 +377,14 @@ class CouncilGen(_StackedNet):
         ops = self.ops
         adain = self._mlp(style, saved, sl)
         x = content
-        for blk in self.dec_res:
+        nres, nup = len(self.dec_res), len(self.dec_up)
+        for r, blk in enumerate(self.dec_res):
             res = x
             x = self._conv_norm(x, blk[0], sl, adain, ACT_RELU, None, False, saved)
-            x = self._conv_norm(x, blk[1], sl, adain, ACT_NONE, res, False, saved)
-        for a, b in self.dec_up:
-            x = self._conv_norm(x, a, sl, adain, ACT_RELU, None, True, saved)
-            x = self._conv_norm(x, b, sl, adain, ACT_RELU, None, False, saved)
+            x = self._conv_norm(x, blk[1], sl, adain, ACT_NONE, res, r == nres - 1 and nup > 0, saved)
+        for u, (a, b) in enumerate(self.dec_up):
+            x = self._conv_norm(x, a, sl, adain, ACT_RELU, None, False, saved)
+            x = self._conv_norm(x, b, sl, adain, ACT_RELU, None, u + 1 < nup, saved)
         acts = [x]
         for li, s in enumerate(self.head):
             w, b = self._w(s, sl)
@@ -409,10 +413,14 @@ class CouncilGen(_StackedNet):
         # upsampling blocks, last to first
         recs = dec_saved  # one record per conv in forward order: dec_res (2*nr) then dec_up (2*nd)
         k = len(recs) - 1
-        for a, b in reversed(self.dec_up):
-            d = self._conv_norm_bwd(d, b, recs[k], adain, d_adain, ACT_RELU, False, None)
-            d = self._conv_norm_bwd(d, a, recs[k - 1], adain, d_adain, ACT_RELU, True, None)
+        nup = len(self.dec_up)
+        for u in range(nup - 1, -1, -1):
+            a, b = self.dec_up[u]
+            d = self._conv_norm_bwd(d, b, recs[k], adain, d_adain, ACT_RELU, u + 1 < nup, None)
+            d = self._conv_norm_bwd(d, a, recs[k - 1], adain, d_adain, ACT_RELU, False, None)
             k -= 2
+        if nup > 0:
+            d = ops.upsample2x_bwd(d)  # the last residual block's output was written upsampled
         for blk in reversed(self.dec_res):
             d_out = d
             d = self._conv_norm_bwd(d_out, blk[1], recs[k], adain, d_adain, ACT_NONE, False, None)

@@ -38,6 +38,7 @@ _SIGS = {
     'cg_in_stats': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_norm_act_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp]),
     'cg_norm_act_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp, C.c_size_t, _fp]),
+    'cg_upsample2x_bwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_mask_head_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_mask_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_avgpool_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
@@ -122,6 +123,31 @@ class CudaOps:
     def set_tensor_core_mode(self, mode):
         return self.lib.cg_set_tensor_core_mode(int(mode))
 
+    # -- live per-kernel timing (bench.py roofline): CUDA events on the launching stream ----------
+    _timing = None
+
+    def start_timing(self):
+        self._timing = {}
+
+    def stop_timing(self):
+        """-> {kernel key: (total ms, launches, algorithmic FLOPs per launch)} for the timed conv launches."""
+        rec, self._timing = self._timing or {}, None
+        torch.cuda.synchronize(self.device)
+        return {k: (sum(a.elapsed_time(b) for a, b in evs), len(evs), fl) for k, (evs, fl) in rec.items()}
+
+    def _timed(self, kind, g, fn):
+        if self._timing is None:
+            return fn()
+        key = '%s G%d B%d %dx%d Cin%d Cout%d k%d s%d%s' % (kind, g.G, g.B, g.H, g.W, g.Cin, g.Cout, g.KH, g.stride,
+                                                          ' ups' if g.ups else '')
+        flops = 2.0 * g.G * g.B * g.Ho * g.Wo * g.Cout * g.KH * g.KW * g.Cin
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self._timing.setdefault(key, ([], flops))[0].append((e0, e1))
+        return out
+
     @staticmethod
     def _chk(*ts):
         for t in ts:
@@ -141,8 +167,8 @@ class CudaOps:
         g = self._geom(x.shape, w, stride, pad, ups)
         y = self.empty(g.G, g.B, g.Ho, g.Wo, g.Cout)
         ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 0))
-        self._ck(self.lib.cg_conv_fwd(C.byref(g), _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ws), ws.numel(),
-                                      self._stream()), 'cg_conv_fwd')
+        self._timed('conv_fwd', g, lambda: self._ck(self.lib.cg_conv_fwd(
+            C.byref(g), _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ws), ws.numel(), self._stream()), 'cg_conv_fwd'))
         return y
 
     def conv_dgrad(self, dy, w, x_shape, stride, pad, ups=False, addend=None, mask_src=None, mask_slope=0.0):
@@ -152,8 +178,9 @@ class CudaOps:
         assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout), (tuple(dy.shape), (g.G, g.B, g.Ho, g.Wo, g.Cout))
         dx = self.empty(g.G, g.B, g.H, g.W, g.Cin)
         ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 1))
-        self._ck(self.lib.cg_conv_dgrad(C.byref(g), _p(dy), _p(w), _p(dx), _p(addend), _p(mask_src), mask_slope,
-                                        _p(ws), ws.numel(), self._stream()), 'cg_conv_dgrad')
+        self._timed('conv_dgrad', g, lambda: self._ck(self.lib.cg_conv_dgrad(
+            C.byref(g), _p(dy), _p(w), _p(dx), _p(addend), _p(mask_src), mask_slope, _p(ws), ws.numel(), self._stream()),
+            'cg_conv_dgrad'))
         return dx
 
     def conv_wgrad(self, x, dy, dw, db, stride, pad, ups=False):
@@ -162,8 +189,8 @@ class CudaOps:
         g = self._geom(x.shape, dw, stride, pad, ups)
         assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout)
         ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 2))
-        self._ck(self.lib.cg_conv_wgrad(C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(),
-                                        self._stream()), 'cg_conv_wgrad')
+        self._timed('conv_wgrad', g, lambda: self._ck(self.lib.cg_conv_wgrad(
+            C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), self._stream()), 'cg_conv_wgrad'))
 
     # -- instance norm / AdaIN --------------------------------------------------------------------
     def in_stats(self, y, eps=1e-5):
@@ -194,6 +221,14 @@ class CudaOps:
                                           G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
                  'cg_norm_act_bwd')
         return dy
+
+    def upsample2x_bwd(self, d_up):
+        self._chk(d_up)
+        G, B, H2, W2, Cc = d_up.shape
+        dx = self.empty(G, B, H2 // 2, W2 // 2, Cc)
+        self._ck(self.lib.cg_upsample2x_bwd(_p(d_up), _p(dx), G * B, H2 // 2, W2 // 2, Cc, self._stream()),
+                 'cg_upsample2x_bwd')
+        return dx
 
     # -- mask head --------------------------------------------------------------------------------
     def mask_head_fwd(self, h, x_in):

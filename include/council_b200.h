@@ -94,6 +94,9 @@ int cg_norm_act_bwd(const float* dz, const float* y, const float* mean, const fl
                     const float* adain, int P, int off, float* dy, float* d_adain, int G, int B,
                     int H, int W, int C, int act, int ups, void* ws, size_t ws_bytes, void* stream);
 
+/* backward of nn.Upsample(scale_factor=2) (networks.py:385): dx[N][H][W][C] = 2x2 fan-in sum of d_up[N][2H][2W][C] */
+int cg_upsample2x_bwd(const float* d_up, float* dx, int N, int H, int W, int C, void* stream);
+
 /* ---- attention-mask head (Decoder_V2_atten.forward networks.py:398-407) ----------------------- */
 /* h[G][B][HW][12] = tanh output of dec.model.9; x_in[B][HW][4] (shared); outputs padded to 4 ch. */
 int cg_mask_head_fwd(const float* h, const float* x_in, float* x_fake, float* mask, int G, int B,

@@ -128,6 +128,10 @@ class TorchOps:
             dy, = torch.autograd.grad(z, [yy], dz)
         return dy.contiguous()
 
+    def upsample2x_bwd(self, d_up):
+        G, B, H2, W2, Cc = d_up.shape
+        return d_up.reshape(G, B, H2 // 2, 2, W2 // 2, 2, Cc).sum(dim=(3, 5)).contiguous()
+
     # -- mask head --------------------------------------------------------------------------------
     @staticmethod
     def _mask_head(h, x_in):

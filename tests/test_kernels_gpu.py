@@ -1,0 +1,239 @@
+"""Per-kernel parity: every C-ABI op (through ctypes, council_gan_b200.ops.CudaOps) against the plain
+PyTorch reference of the same op (tests/ops_torch.py) evaluated in float64 on the same device.
+
+Tolerances: the SIMT kernels compute in exact fp32 -> 2e-5 relative to the tensor's max magnitude.
+The tensor-core path (TF32 operands, fp32 accumulate) is compared at 3e-3 (10-bit mantissa operands).
+"""
+import pytest
+import torch
+
+from ops_torch import TorchOps
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from council_gan_b200.ops import CudaOps
+    return CudaOps(DEV)
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return TorchOps(DEV, torch.float64)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def d(t):
+    return None if t is None else t.double()
+
+
+def check(got, want, tol=2e-5, what=''):
+    want = want.to(torch.float64)
+    err = (got.double() - want).abs().max().item()
+    mag = want.abs().max().item() + 1e-30
+    assert err <= tol * mag + 1e-7, '%s: max err %.3e vs magnitude %.3e' % (what, err, mag)
+
+
+# (name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups)
+CONV_CASES = [
+    ('enc0_7x7_img', 2, 1, 2, 16, 16, 4, 64, 7, 1, 3, False),
+    ('enc1_4x4s2', 2, 2, 2, 16, 16, 64, 128, 4, 2, 1, False),
+    ('res_3x3', 2, 2, 1, 8, 8, 256, 256, 3, 1, 1, False),
+    ('up_3x3_ups', 2, 2, 2, 8, 8, 128, 64, 3, 1, 1, True),
+    ('head_1x1', 2, 2, 2, 16, 16, 64, 64, 1, 1, 0, False),
+    ('head_1x1_12', 2, 2, 2, 16, 16, 64, 12, 1, 1, 0, False),
+    ('dis0_4x4s2_img', 3, 3, 2, 16, 16, 4, 64, 4, 2, 1, False),
+    ('disc0_3x3_pair', 2, 2, 3, 12, 12, 8, 64, 3, 1, 1, False),
+    ('dis_out_1x1', 2, 2, 4, 4, 4, 512, 1, 1, 1, 0, False),
+    ('mlp_linear', 2, 1, 3, 1, 1, 64, 256, 1, 1, 0, False),
+    ('mlp_linear_big', 2, 2, 3, 1, 1, 256, 5888, 1, 1, 0, False),
+    ('odd_sizes', 1, 1, 1, 10, 14, 8, 20, 3, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize('tc', [0, 1])
+def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
+    name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups = case
+    ops.set_tensor_core_mode(tc)
+    tol = 2e-5 if tc == 0 else 4e-3
+    try:
+        x = rnd(Gx, B, H, W, Cin, seed=1)
+        w = rnd(G, Cout, K, K, Cin, seed=2, scale=0.1)
+        b = rnd(G, Cout, seed=3)
+        for act in (0, 1, 2, 3):
+            y = ops.conv_fwd(x, w, b, stride, pad, ups=ups, act=act, slope=0.2)
+            check(y, ref.conv_fwd(d(x), d(w), d(b), stride, pad, ups=ups, act=act, slope=0.2), tol, name + ' fwd act%d' % act)
+        y = ops.conv_fwd(x, w, None, stride, pad, ups=ups)
+        check(y, ref.conv_fwd(d(x), d(w), None, stride, pad, ups=ups), tol, name + ' fwd nobias')
+        dy = rnd(*y.shape, seed=4)
+        xs = (G, B, H, W, Cin)
+        add = rnd(*xs, seed=5)
+        msk = rnd(*xs, seed=6)
+        dx = ops.conv_dgrad(dy, w, xs, stride, pad, ups=ups)
+        check(dx, ref.conv_dgrad(d(dy), d(w), xs, stride, pad, ups=ups), tol, name + ' dgrad')
+        dx = ops.conv_dgrad(dy, w, xs, stride, pad, ups=ups, addend=add, mask_src=msk, mask_slope=0.2)
+        check(dx, ref.conv_dgrad(d(dy), d(w), xs, stride, pad, ups=ups, addend=d(add), mask_src=d(msk), mask_slope=0.2),
+              tol, name + ' dgrad+addend+mask')
+        dw, db = torch.full_like(w, 7.0), torch.full_like(b, 7.0)
+        ops.conv_wgrad(x, dy, dw, db, stride, pad, ups=ups)
+        rw, rb = torch.zeros_like(w, dtype=torch.float64), torch.zeros_like(b, dtype=torch.float64)
+        ref.conv_wgrad(d(x), d(dy), rw, rb, stride, pad, ups=ups)
+        check(dw, rw, tol, name + ' wgrad')
+        check(db, rb, tol, name + ' bias grad')
+    finally:
+        ops.set_tensor_core_mode(1)
+
+
+def test_conv_wgrad_split_k_large(ops, ref):
+    """Many pixels, few output tiles -> split-K with the deterministic two-phase reduction."""
+    x = rnd(1, 2, 64, 64, 8, seed=1)
+    dy = rnd(2, 2, 64, 64, 16, seed=2)
+    dw = ops.empty(2, 16, 3, 3, 8)
+    db = ops.empty(2, 16)
+    ops.conv_wgrad(x, dy, dw, db, 1, 1)
+    dw2 = torch.empty_like(dw)
+    ops.conv_wgrad(x, dy, dw2, None, 1, 1)
+    assert torch.equal(dw, dw2), 'wgrad must be run-to-run deterministic'
+    rw, rb = torch.zeros_like(dw, dtype=torch.float64), torch.zeros_like(db, dtype=torch.float64)
+    ref.conv_wgrad(d(x), d(dy), rw, rb, 1, 1)
+    check(dw, rw, 2e-5, 'wgrad split-K')
+    check(db, rb, 2e-5, 'bias grad')
+
+
+@pytest.mark.parametrize('C', [64, 128, 256])
+@pytest.mark.parametrize('adain_on,res_on,act,ups', [(False, False, 1, False), (True, True, 0, False),
+                                                     (True, False, 1, True), (False, True, 0, False)])
+def test_norm_fwd_bwd(ops, ref, C, adain_on, res_on, act, ups):
+    G, B, H, W = 2, 2, 12, 10
+    y = rnd(G, B, H, W, C, seed=1, scale=2.0) + 0.5
+    P = 4 * C + 16
+    off = 8
+    adain = rnd(G, B, P, seed=2) if adain_on else None
+    res = rnd(G, B, H, W, C, seed=3) if res_on else None
+    mean, rstd = ops.in_stats(y)
+    rm, rr = ref.in_stats(d(y))
+    check(mean, rm, 2e-5, 'mean')
+    check(rstd, rr, 2e-5, 'rstd')
+    z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups)
+    check(z, ref.norm_act_fwd(d(y), rm, rr, d(adain), off, d(res), act, ups), 3e-5, 'norm fwd')
+    dz = rnd(*z.shape, seed=4)
+    d_adain = ops.zeros(G, B, P) if adain_on else None
+    dy = ops.norm_act_bwd(dz, y, mean, rstd, adain, off, act, ups, d_adain)
+    r_dad = torch.zeros(G, B, P, dtype=torch.float64, device=DEV) if adain_on else None
+    rdy = ref.norm_act_bwd(d(dz), d(y), rm, rr, d(adain), off, act, ups, r_dad)
+    check(dy, rdy, 1e-4, 'norm bwd dy')
+    if adain_on:
+        check(d_adain, r_dad, 1e-4, 'norm bwd d_adain')
+
+
+def test_mask_head(ops, ref):
+    G, B, H, W = 2, 2, 9, 7
+    h = torch.tanh(rnd(G, B, H, W, 12, seed=1, scale=0.3))
+    x_in = rnd(1, B, H, W, 4, seed=2)
+    x_in[..., 3] = 0
+    xf, mask = ops.mask_head_fwd(h, x_in)
+    rxf, rmask = ref.mask_head_fwd(d(h), d(x_in))
+    check(xf, rxf, 2e-5, 'x_fake')
+    check(mask, rmask, 2e-5, 'mask')
+    assert float(xf[..., 3].abs().max()) == 0 and float(mask[..., 3].abs().max()) == 0
+    dxf, dm = rnd(G, B, H, W, 4, seed=3), rnd(G, B, H, W, 4, seed=4)
+    for dmask in (None, dm):
+        got = ops.mask_head_bwd(h, x_in, dxf, dmask)
+        want = ref.mask_head_bwd(d(h), d(x_in), d(dxf), d(dmask))
+        check(got, want, 5e-5, 'mask head bwd')
+
+
+def test_image_helpers(ops, ref):
+    G, B, H, W = 2, 3, 8, 12
+    x = rnd(G, B, H, W, 8, seed=1)
+    check(ops.avgpool_fwd(x), ref.avgpool_fwd(d(x)), 2e-5, 'avgpool fwd')
+    dy = rnd(G, B, H // 2, W // 2, 8, seed=2)
+    for acc in (False, True):
+        dx = rnd(G, B, H, W, 4, seed=3)
+        rdx = d(dx).clone()
+        ops.avgpool_bwd(dy, dx, 4, acc)
+        ref.avgpool_bwd(d(dy), rdx, 4, acc)
+        check(dx, rdx, 2e-5, 'avgpool bwd acc=%s' % acc)
+    dst, src = rnd(G, B, H, W, 4, seed=4), rnd(G, B, H, W, 8, seed=5)
+    rdst = d(dst).clone()
+    ops.acc_slice(dst, src, 4)
+    ref.acc_slice(rdst, d(src), 4)
+    check(dst, rdst, 1e-6, 'acc_slice')
+    pool = rnd(5, H, W, 4, seed=6)
+    idx = torch.tensor([[0, 4, 2, 2, 1, 3], [3, 3, 0, 1, 4, 2]], dtype=torch.int32, device=DEV)
+    x_in = rnd(1, 3, H, W, 4, seed=7)
+    for xi in (None, x_in):
+        got = ops.gather_images(pool, idx, xi, 2, 6)
+        want = ref.gather_images(d(pool), idx, d(xi), 2, 6)
+        assert torch.equal(got.double(), want)
+    img = rnd(3, 3, H, W, seed=8)
+    nhwc = ops.nchw_to_nhwc(img, 4)
+    assert torch.equal(nhwc.double(), ref.nchw_to_nhwc(d(img), 4))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc, 3), img)
+
+
+def test_losses(ops, ref):
+    G, nseg, B, h, w = 3, 3, 2, 5, 4
+    out = rnd(G, nseg * B, h, w, 1, seed=1)
+    targets = torch.tensor([0.0, 1.0, 1.0], device=DEV)
+    weights = torch.tensor([2.0, 0.5, 0.5], device=DEV)
+    loss = torch.full((G,), 3.0, device=DEV)
+    rloss = loss.double().clone()
+    for acc in (False, True):
+        sums = ops.lsgan_fwd(out, targets, weights, nseg, loss, acc)
+        rs = ref.lsgan_fwd(d(out), d(targets), d(weights), nseg, rloss, acc)
+        check(sums, rs, 2e-5, 'lsgan sums')
+        check(loss, rloss, 2e-5, 'lsgan loss')
+    coef = rnd(G, nseg, seed=2)
+    check(ops.lsgan_bwd(out, targets, coef, nseg), ref.lsgan_bwd(d(out), d(targets), d(coef), nseg), 2e-5, 'lsgan bwd')
+    mask = torch.sigmoid(rnd(G, 2, 11, 9, 4, seed=3, scale=3.0))
+    mask[..., 3] = 0
+    check(ops.focus_fwd(mask, 0.5, 0.01), ref.focus_fwd(d(mask), 0.5, 0.01), 5e-5, 'focus sums')
+    fc = rnd(G, 3, seed=4)
+    check(ops.focus_bwd(mask, fc, 0.5, 0.01), ref.focus_bwd(d(mask), d(fc), 0.5, 0.01), 5e-5, 'focus bwd')
+    fc[:, 2] = 0  # TV off (male2female config)
+    check(ops.focus_bwd(mask, fc, 0.5, 0.01), ref.focus_bwd(d(mask), d(fc), 0.5, 0.01), 5e-5, 'focus bwd no tv')
+
+
+def test_adam(ops, ref):
+    n = 100003
+    p, g = rnd(n, seed=1), rnd(n, seed=2, scale=0.01)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    rp, rm, rv = d(p).clone(), d(m).clone(), d(v).clone()
+    for step in (1, 2, 3):
+        ops.adam_step(p, g, m, v, 1e-4, 0.5, 0.999, 1e-8, 1e-4, step)
+        ref.adam_step(rp, d(g), rm, rv, 1e-4, 0.5, 0.999, 1e-8, 1e-4, step)
+    assert (p.double() - rp).abs().max().item() < 1e-6  # a few fp32 ulps of |p| ~ 1.5 over three steps
+    check(m, rm, 2e-5, 'exp_avg')
+    check(v, rv, 2e-5, 'exp_avg_sq')
+
+
+# ---- size-independent properties at the BASELINE sizes (256x256, council of 4, batch 8) ------------------
+def test_full_size_adjoint_identities(ops):
+    """<conv(x), dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)> for the dominant 3x3 256->256 layer at the
+    male2female B=8 shape (G=4, 64x64 maps), and instance-norm output statistics."""
+    G, B, H, W, C = 4, 8, 64, 64, 256
+    x = rnd(G, B, H, W, C, seed=1)
+    w = rnd(G, C, 3, 3, C, seed=2, scale=0.02)
+    dy = rnd(G, B, H, W, C, seed=3)
+    y = ops.conv_fwd(x, w, None, 1, 1)
+    dx = ops.conv_dgrad(dy, w, x.shape, 1, 1)
+    dw = ops.empty(*w.shape)
+    ops.conv_wgrad(x, dy, dw, None, 1, 1)
+    a = (y.double() * dy.double()).sum().item()
+    b = (x.double() * dx.double()).sum().item()
+    c = (w.double() * dw.double()).sum().item()
+    assert abs(a - b) <= 2e-3 * abs(a) and abs(a - c) <= 2e-3 * abs(a), (a, b, c)
+    mean, rstd = ops.in_stats(y)
+    z = ops.norm_act_fwd(y, mean, rstd, None, 0, None, 0, False)
+    zm = z.double().mean(dim=(2, 3))
+    zv = z.double().var(dim=(2, 3), unbiased=False)
+    assert zm.abs().max().item() < 1e-4 and (zv - 1).abs().max().item() < 1e-3
