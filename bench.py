@@ -257,6 +257,8 @@ def main():
             'dtype': 'tf32' if args.tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
             'gpu_launches': int(launches), 'roofline': roofline,
             'step_algorithmic_tflops': alg_tflop / (ms_per_step * 1e-3) / world,
+            'kernel_times_ms_per_step': ({k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:14]}
+                                         if ktimes else None),
             'losses': {'gen': [float(v) for v in trainer.loss_gen_total_s], 'dis': [float(v) for v in trainer.loss_dis_total_s]}}
     if not args.no_cpu_baseline:
         rate, dt, cores = cpu_oracle_rate(args.workload, 1, 1)

@@ -68,7 +68,8 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
         if (g_tc_mode && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }
     }
     if (which == 2) {
-        size_t a = simt_wgrad_ws(*g), b = colsum_ws(g->G, d.Mpix, g->Cout);
+        size_t a = (g_tc_mode && tc_wgrad_supported(*g)) ? tc_wgrad_ws(*g) : simt_wgrad_ws(*g);
+        size_t b = colsum_ws(g->G, d.Mpix, g->Cout);
         need = a > b ? a : b;
     }
     return need;
@@ -101,7 +102,11 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
                              size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = simt_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;
+    if (g_tc_mode && tc_wgrad_supported(*g)) {
+        if (int rc = tc_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;
+    } else {
+        if (int rc = simt_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;
+    }
     if (db) {
         ConvDims d = conv_dims(*g);
         return colsum(dy, db, g->G, d.Mpix, g->Cout, ws, ws_bytes, st);

@@ -79,4 +79,9 @@ size_t tc_dgrad_ws(const cg_conv_geom& g);
 int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float* dx, const float* addend,
                   const float* mask_src, float mask_slope, void* ws, size_t ws_bytes, cudaStream_t st);
 
+bool tc_wgrad_supported(const cg_conv_geom& g);
+size_t tc_wgrad_ws(const cg_conv_geom& g);
+int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+
 }  // namespace cg

@@ -272,6 +272,14 @@ class Council_Trainer(nn.Module):
     def _src(self, d, a, b):
         return a if d == 'a2b' else b
 
+    def _global_mean(self, t):
+        """Reported loss values are means over the GLOBAL minibatch (equal shards): average over ranks."""
+        dist = _dist()
+        if dist is not None and self.world > 1:
+            dist.all_reduce(t)
+            t = t / self.world
+        return t
+
     # ==================================================================================================
     # dis_update   (trainer_council.py:735-780)
     # ==================================================================================================
@@ -315,6 +323,7 @@ class Council_Trainer(nn.Module):
                 coef = self._const(('c2', cf, N), [[cf, cf]] * N)
                 d_outs.append(ops.lsgan_bwd(out, targets, coef, 2))
             dis.backward(d_outs, saved, want_wgrad=True, want_dx=False)
+        total = self._global_mean(total)
         self._loss_dis_total = total
         self.loss_dis_total_s = _LossList(total[i] for i in range(N))
         self._adam('dis')
@@ -404,6 +413,7 @@ class Council_Trainer(nn.Module):
                 coef = self._const(('ck', K, wk, cf, N), [[wk * K * cf] + [wk * cf] * K] * N)
                 d_outs.append(ops.lsgan_bwd(out, targets, coef, 1 + K))
             disc.backward(d_outs, saved, want_wgrad=True, want_dx=False)
+        total = self._global_mean(total)
         self._loss_dis_council_total = total
         self.loss_dis_council_total_s = _LossList(total[i] for i in range(N))
         self._adam('dis_council')

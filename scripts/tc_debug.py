@@ -21,6 +21,13 @@ CASES = [
     ('dgrad_1x1', 'dgrad', 2, 2, 2, 16, 16, 64, 64, 1, 1, 0),
     ('dgrad_4x4s2', 'dgrad', 2, 2, 2, 32, 32, 64, 128, 4, 2, 1),
     ('dgrad_4x4s2_big', 'dgrad', 2, 2, 2, 32, 32, 256, 512, 4, 2, 1),
+    ('wgrad_1x1_c32_o128', 'wgrad', 1, 1, 1, 16, 16, 32, 128, 1, 1, 0),
+    ('wgrad_1x1_c64_o64', 'wgrad', 2, 2, 2, 16, 16, 64, 64, 1, 1, 0),
+    ('wgrad_3x3_c64_o128', 'wgrad', 1, 1, 2, 16, 16, 64, 128, 3, 1, 1),
+    ('wgrad_3x3_c256_o256', 'wgrad', 2, 2, 2, 32, 32, 256, 256, 3, 1, 1),
+    ('wgrad_4x4s2_c128_o256', 'wgrad', 2, 2, 2, 32, 32, 128, 256, 4, 2, 1),
+    ('wgrad_4x4s2_c256_o512', 'wgrad', 2, 2, 4, 32, 32, 256, 512, 4, 2, 1),
+    ('wgrad_shared_x', 'wgrad', 2, 1, 2, 16, 16, 64, 128, 3, 1, 1),
 ]
 
 
@@ -44,6 +51,18 @@ def run_case(idx):
         want = ref.conv_fwd(x.double(), w.double(), b.double(), stride, pad)
         ops.set_tensor_core_mode(0)
         y0 = ops.conv_fwd(x, w, b, stride, pad)
+    elif kind == 'wgrad':
+        Ho = (H + 2 * pad - K) // stride + 1
+        dy = torch.randn(G, B, Ho, Ho * W // H, Cout, generator=g).cuda()
+        ops.set_tensor_core_mode(1)
+        y = torch.zeros_like(w)
+        ops.conv_wgrad(x, dy, y, None, stride, pad)
+        torch.cuda.synchronize()
+        want = torch.zeros_like(w, dtype=torch.float64)
+        ref.conv_wgrad(x.double(), dy.double(), want, None, stride, pad)
+        ops.set_tensor_core_mode(0)
+        y0 = torch.zeros_like(w)
+        ops.conv_wgrad(x, dy, y0, None, stride, pad)
     else:
         Ho = (H + 2 * pad - K) // stride + 1
         dy = torch.randn(G, B, Ho, Ho * W // H, Cout, generator=g).cuda()
@@ -70,9 +89,12 @@ if __name__ == '__main__':
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
+        only = os.environ.get('TC_ONLY', '')
         for i, c in enumerate(CASES):
+            if only and only not in c[1]:
+                continue
             try:
-                r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=90)
+                r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=45)
                 lines = [l for l in r.stdout.splitlines() if l.startswith('RESULT')]
                 print(c[0], lines[0] if lines else 'NO RESULT rc=%d %s' % (r.returncode, (r.stderr or '')[-600:]), flush=True)
             except subprocess.TimeoutExpired:
