@@ -102,7 +102,7 @@ def cpu_oracle_rate(workload, steps, warmup):
     import council_oracle as co
     hp, n, b, size, it = load_hp(workload)
     hp['batch_size'] = 1
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, int(os.environ.get('COUNCIL_CPU_THREADS', '32')))
     torch.set_num_threads(cores)
     states = co.synth_all_states(hp, seed=7)
     tr = co.OracleTrainer(hp, states)
@@ -257,7 +257,7 @@ def main():
             'dtype': 'tf32' if args.tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
             'gpu_launches': int(launches), 'roofline': roofline,
             'step_algorithmic_tflops': alg_tflop / (ms_per_step * 1e-3) / world,
-            'kernel_times_ms_per_step': ({k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:14]}
+            'kernel_times_ms_per_step': ({k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:60]}
                                          if ktimes else None),
             'losses': {'gen': [float(v) for v in trainer.loss_gen_total_s], 'dis': [float(v) for v in trainer.loss_dis_total_s]}}
     if not args.no_cpu_baseline:

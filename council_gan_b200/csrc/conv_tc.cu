@@ -120,6 +120,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;            // SWIZZLE_128B
     return d;
 }
+// K-major rows of 8 fp32 (32 bytes), 32-byte swizzle (cute Layout_K_SW32): 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+    return d;
+}
 // instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -151,6 +161,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
@@ -174,6 +195,8 @@ struct TcParams {
     int B, P, Q;                    // output grid per class: P x Q pixels per image
     int Cin, Cout, KH, KW, stride;  // KH,KW: taps per class
     int bn;                         // N tile
+    int bk;                         // K elements per stage: 32 (128-byte swizzled rows) or 8 (32-byte rows, Cin = 8)
+    int n_store;                    // output channels actually stored per N tile (== bn except the 8-lane image gradient)
     int out_H, out_W, out_sh, out_sw;  // full output spatial size and class strides
     int w_rows_per_group;           // weight rows per group (ncls * Cout for dgrad classes)
     float* y; const float* bias; const float* addend; const float* mask_src;
@@ -185,9 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = TC_BM * TC_BK * 4;
-    const int b_bytes = p.bn * TC_BK * 4;
+    const int a_bytes = TC_BM * p.bk * 4;
+    const int b_bytes = ((p.bn * p.bk * 4) + 1023) & ~1023;
     const int stage_bytes = a_bytes + b_bytes;
+    const int tx_bytes = a_bytes + p.bn * p.bk * 4;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tfull_bar = empty_bar + p.stages;
@@ -195,9 +219,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int MT = (p.B * p.P * p.Q + TC_BM - 1) / TC_BM;  // pixel tiles per (group, class)
-    const int NT = p.Cout / p.bn;
+    const int NT = (p.Cout + p.bn - 1) / p.bn;
     const int tiles = p.G * p.ncls * NT * MT;
-    const int kchunks = p.Cin / TC_BK;
+    const int kchunks = p.Cin / p.bk;
     const int kiters = p.KH * p.KW * kchunks;
     const int tmem_cols = 2 * p.bn < 32 ? 32 : 2 * p.bn;
 
@@ -254,10 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                            tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa, kc * TC_BK, w_coord, h_coord, n_coord,
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)tx_bytes);
+                            tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa, kc * p.bk, w_coord, h_coord, n_coord,
                                                (uint16_t)kw, (uint16_t)kh);
-                            tma_load_2d(&p.bmap, &full_bar[stage], sb, ((kh * p.KW + kw) * kchunks + kc) * TC_BK, wrow);
+                            tma_load_2d(&p.bmap, &full_bar[stage], sb, ((kh * p.KW + kw) * kchunks + kc) * p.bk, wrow);
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
             }
@@ -279,10 +303,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_fence_after();
                     uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     uint32_t sb = sa + a_bytes;
-                    uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    uint64_t bdesc = make_kmajor_sw128_desc(sb);
-#pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; kk++) {
+                    uint64_t adesc = p.bk == 32 ? make_kmajor_sw128_desc(sa) : make_kmajor_sw32_desc(sa);
+                    uint64_t bdesc = p.bk == 32 ? make_kmajor_sw128_desc(sb) : make_kmajor_sw32_desc(sb);
+                    const int nmma = p.bk / 8;
+                    for (int kk = 0; kk < nmma; kk++) {
                         // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzled row: +2 in the 16-byte address field
                         umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
                     }
@@ -318,9 +342,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 int rem = (int)(m - (long)img * PQ);
                 int pp = rem / p.Q, qq = rem - pp * p.Q;
                 long pix = ((long)(g * p.B + img) * p.out_H + (pp * p.out_sh + cl.out_h0)) * p.out_W + (qq * p.out_sw + cl.out_w0);
-                out_off = pix * p.Cout + nt * p.bn;
+                out_off = pix * p.Cout + nt * p.n_store;
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
+            if (p.n_store < 32) {
+                // image-side data gradient: 16 accumulator columns, the first n_store (8) are the image lanes
+                float v[32];
+                tmem_ld16(taddr, v);
+                if (valid) {
+                    for (int j = 0; j < p.n_store; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (p.addend) {
+                            float4 a = __ldg(reinterpret_cast<const float4*>(p.addend + out_off + j));
+                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                        }
+                        if (p.mask_src) {
+                            float4 a = __ldg(reinterpret_cast<const float4*>(p.mask_src + out_off + j));
+                            o.x *= a.x > 0.f ? 1.f : p.slope; o.y *= a.y > 0.f ? 1.f : p.slope;
+                            o.z *= a.z > 0.f ? 1.f : p.slope; o.w *= a.w > 0.f ? 1.f : p.slope;
+                        }
+                        *reinterpret_cast<float4*>(p.y + out_off + j) = o;
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < p.bn; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
@@ -371,14 +415,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long ktot, int bn) {
+static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long ktot, int bn, int bk = TC_BK) {
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)w, dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(weights rows=%ld ktot=%ld bn=%d) failed: %d", rows, ktot, bn, (int)r);
         return CG_ERR_CUDA;
@@ -389,15 +433,15 @@ static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long 
 // activation [N][H][W][C] viewed by TMA as (C, W, H, N); bounding box corners as in CUTLASS
 // (cutlass/conv/collective/detail.hpp compute_lower/upper_corner_whd): lower = -pad_lo, upper = pad_hi - (K-1).
 static int encode_act_map(CUtensorMap* map, const float* x, long N, int H, int W, int C, int lo_w, int lo_h, int up_w, int up_h,
-                          int stride) {
+                          int stride, int bk = TC_BK) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     int lower[2] = {lo_w, lo_h};
     int upper[2] = {up_w, up_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, TC_BK, TC_BM, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, bk, TC_BM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeIm2col(N=%ld H=%d W=%d C=%d corners %d,%d / %d,%d stride %d) failed: %d", N, H, W, C, lo_w, lo_h,
                   up_w, up_h, stride, (int)r);
@@ -420,7 +464,7 @@ bool tc_fwd_supported(const cg_conv_geom& g) {
     init_driver();
     if (!g_encode_tiled || !g_encode_im2col) return false;
     if (g.ups) return false;
-    if (g.Cin % TC_BK != 0) return false;
+    if (g.Cin % TC_BK != 0 && g.Cin != 8) return false;
     if (pick_bn(g.Cout) == 0) return false;
     if (g.pad > 120 || g.KH > 120) return false;
     if ((long)g.B * g.Ho * g.Wo < TC_BM) return false;  // tiny maps: the SIMT kernel is fine
@@ -428,10 +472,11 @@ bool tc_fwd_supported(const cg_conv_geom& g) {
 }
 
 static int launch_tc(TcParams& p, cudaStream_t st) {
-    int a_bytes = TC_BM * TC_BK * 4, b_bytes = p.bn * TC_BK * 4;
+    int a_bytes = TC_BM * p.bk * 4, b_bytes = ((p.bn * p.bk * 4) + 1023) & ~1023;
     int stage_bytes = a_bytes + b_bytes;
     int stages = (200 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
+    if (stages > 12) stages = 12;
+    if (p.n_store == 0) p.n_store = p.bn;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
     static bool attr_set = false;
@@ -444,7 +489,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
         attr_set = true;
     }
     int MT = cdiv((long)p.B * p.P * p.Q, TC_BM);
-    long tiles = (long)p.G * p.ncls * (p.Cout / p.bn) * MT;
+    long tiles = (long)p.G * p.ncls * ((p.Cout + p.bn - 1) / p.bn) * MT;
     int grid = (int)(tiles < g_sm_count ? tiles : g_sm_count);
     conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
     return check_launch("conv_tc_kernel");
@@ -455,10 +500,12 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
     init_driver();
     TcParams p{};
     p.bn = pick_bn(g.Cout);
+    p.bk = g.Cin % TC_BK == 0 ? TC_BK : 8;
     long ktot = (long)g.KH * g.KW * g.Cin;
-    if (int rc = encode_weights_map(&p.bmap, w, (long)g.G * g.Cout, ktot, p.bn)) return rc;
+    if (int rc = encode_weights_map(&p.bmap, w, (long)g.G * g.Cout, ktot, p.bn, p.bk)) return rc;
     long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
-    if (int rc = encode_act_map(&p.cls[0].amap, x, nimg, g.H, g.W, g.Cin, -g.pad, -g.pad, g.pad - (g.KW - 1), g.pad - (g.KH - 1), g.stride))
+    if (int rc = encode_act_map(&p.cls[0].amap, x, nimg, g.H, g.W, g.Cin, -g.pad, -g.pad, g.pad - (g.KW - 1), g.pad - (g.KH - 1), g.stride,
+                                p.bk))
         return rc;
     p.cls[0].w0 = -g.pad; p.cls[0].h0 = -g.pad; p.cls[0].out_h0 = 0; p.cls[0].out_w0 = 0; p.cls[0].wrow_off = 0;
     p.ncls = 1;
@@ -482,8 +529,9 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
 // so each class is a forward convolution of dy with transposed+flipped weights wt[g][class][ci][r][s][co],
 // an im2col box with lower corner -padl, and an output written with stride s at offset ihf.
 // ------------------------------------------------------------------------------------------------
-__global__ void dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, long total, int Cout, int Cin, int KH,
-                                              int KW, int s) {
+// CinP >= Cin: rows ci >= Cin are zero (pads the 8 image lanes to the minimum UMMA N of 16)
+__global__ void dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, long total, int Cout, int Cin, int CinP,
+                                              int KH, int KW, int s) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int TH = KH / s, TW = KW / s;
@@ -491,12 +539,12 @@ __global__ void dgrad_weight_transform_kernel(const float* __restrict__ w, float
     long t = i / Cout;
     int ss = (int)(t % TW); t /= TW;
     int r = (int)(t % TH); t /= TH;
-    int ci = (int)(t % Cin); t /= Cin;
+    int ci = (int)(t % CinP); t /= CinP;
     int cls = (int)(t % (s * s));
     int g = (int)(t / (s * s));
     int ph = cls / s, pw = cls - ph * s;
     int kh = ph + s * (TH - 1 - r), kw = pw + s * (TW - 1 - ss);
-    wt[i] = __ldg(w + ((((long)g * Cout + co) * KH + kh) * KW + kw) * Cin + ci);
+    wt[i] = ci < Cin ? __ldg(w + ((((long)g * Cout + co) * KH + kh) * KW + kw) * Cin + ci) : 0.f;
 }
 
 bool tc_dgrad_supported(const cg_conv_geom& g) {
@@ -504,8 +552,8 @@ bool tc_dgrad_supported(const cg_conv_geom& g) {
     if (!g_encode_tiled || !g_encode_im2col) return false;
     int s = g.stride;
     if (s > 2 || g.KH % s || g.KW % s) return false;
-    if (g.Cout % TC_BK != 0) return false;      // K dimension of the dgrad GEMM
-    if (pick_bn(g.Cin) == 0) return false;      // N dimension
+    if (g.Cout % TC_BK != 0) return false;                 // K dimension of the dgrad GEMM
+    if (pick_bn(g.Cin) == 0 && g.Cin != 8) return false;   // N dimension (8 = image lanes, padded to 16)
     int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
     if (Hin % s || Win % s) return false;
     if ((long)g.B * (Hin / s) * (Win / s) < TC_BM) return false;
@@ -513,7 +561,7 @@ bool tc_dgrad_supported(const cg_conv_geom& g) {
 }
 
 size_t tc_dgrad_ws(const cg_conv_geom& g) {
-    size_t wt = (size_t)g.G * g.Cout * g.KH * g.KW * g.Cin * sizeof(float);
+    size_t wt = (size_t)g.G * g.Cout * g.KH * g.KW * (g.Cin == 8 ? 16 : g.Cin) * sizeof(float);
     wt = (wt + 1023) & ~(size_t)1023;
     size_t up = g.ups ? (size_t)g.G * g.B * 4 * g.H * g.W * g.Cin * sizeof(float) : 0;
     return wt + up;
@@ -530,16 +578,19 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
     const int s = g.stride, TH = g.KH / s, TW = g.KW / s, ncls = s * s;
     const int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
     float* wt = (float*)ws;
-    size_t wt_bytes = ((size_t)g.G * g.Cout * g.KH * g.KW * g.Cin * sizeof(float) + 1023) & ~(size_t)1023;
+    const int CinP = g.Cin == 8 ? 16 : g.Cin;
+    size_t wt_bytes = ((size_t)g.G * g.Cout * g.KH * g.KW * CinP * sizeof(float) + 1023) & ~(size_t)1023;
     float* d_seen = g.ups ? (float*)((uint8_t*)ws + wt_bytes) : dx;
-    long total = (long)g.G * g.Cout * g.KH * g.KW * g.Cin;
-    dgrad_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wt, total, g.Cout, g.Cin, g.KH, g.KW, s);
+    long total = (long)g.G * g.Cout * g.KH * g.KW * CinP;
+    dgrad_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wt, total, g.Cout, g.Cin, CinP, g.KH, g.KW, s);
     if (int rc = check_launch("dgrad_weight_transform")) return rc;
 
     TcParams p{};
-    p.bn = pick_bn(g.Cin);
+    p.bn = g.Cin == 8 ? 16 : pick_bn(g.Cin);
+    p.n_store = g.Cin == 8 ? 8 : p.bn;
+    p.bk = TC_BK;
     long ktot = (long)TH * TW * g.Cout;
-    if (int rc = encode_weights_map(&p.bmap, wt, (long)g.G * ncls * g.Cin, ktot, p.bn)) return rc;
+    if (int rc = encode_weights_map(&p.bmap, wt, (long)g.G * ncls * CinP, ktot, p.bn)) return rc;
     for (int c = 0; c < ncls; c++) {
         int ph = c / s, pw = c - ph * s;
         int ihf = ((ph - g.pad) % s + s) % s, iwf = ((pw - g.pad) % s + s) % s;
@@ -549,14 +600,14 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
         if (int rc = encode_act_map(&p.cls[c].amap, dy, (long)g.G * g.B, g.Ho, g.Wo, g.Cout, -padl_w, -padl_h, up_w, up_h, 1)) return rc;
         p.cls[c].w0 = -padl_w; p.cls[c].h0 = -padl_h;
         p.cls[c].out_h0 = ihf; p.cls[c].out_w0 = iwf;
-        p.cls[c].wrow_off = c * g.Cin;
+        p.cls[c].wrow_off = c * CinP;
     }
     p.ncls = ncls;
     p.G = g.G; p.xg_images = g.B;
     p.B = g.B; p.P = Hin / s; p.Q = Win / s;
     p.Cin = g.Cout; p.Cout = g.Cin; p.KH = TH; p.KW = TW; p.stride = 1;
     p.out_H = Hin; p.out_W = Win; p.out_sh = s; p.out_sw = s;
-    p.w_rows_per_group = ncls * g.Cin;
+    p.w_rows_per_group = ncls * CinP;
     p.y = d_seen; p.bias = nullptr;
     p.addend = g.ups ? nullptr : addend; p.mask_src = g.ups ? nullptr : mask_src;
     p.act = CG_ACT_NONE; p.slope = mask_slope;
@@ -574,9 +625,9 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
 // GEMM per (group, 128-cout tile, filter tap, ci tile):  D[128 co][bn ci] += A^T[pixels][co] * B[pixels][ci]
 // with the reduction (K) dimension = pixels.  Both operands are "MN-major" in shared memory: the 32-channel
 // x KP-pixel boxes TMA delivers from the channels-last tensors (dy as a plain 2-D matrix, x through the same
-// im2col map as the forward pass, at the tap's offsets) ARE the canonical 128-byte-swizzled MN-major layout
-// (cute::UMMA Layout_MN_SW128: 32 contiguous MN elements per row, 8 K rows per 1024-byte atom), so no
-// transposition is ever materialised.  The pixel range is split across CTAs (split-K) and reduced in a fixed
+// im2col map as the forward pass, at the tap's offsets, with the 32-byte-atom 128-byte swizzle) ARE the canonical
+// MN-major TF32 layout (cute::UMMA Layout_MN_SW128_32B: 32 contiguous MN elements per row, 4 K rows per 512-byte
+// atom), so no transposition is ever materialised.  The pixel range is split across CTAs (split-K) and reduced in a fixed
 // order by reduce_splits_kernel, keeping the result deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_KP = 32;  // pixels per pipeline stage (4 MMAs of K=8)
@@ -589,13 +640,18 @@ struct WgParams {
     float* out;        // [splits][G][Cout][KH*KW][Cin]
 };
 
+// MN-major TF32 operands admit exactly one shared-memory layout (cutlass sm100_common.inl:92 "for mn-major tf32
+// operands, SW128_32B is the only available smem layout"): rows of 32 contiguous MN elements (128 B), swizzle atom =
+// 4 K-rows x 128 B with 32-byte chunks XOR-ed by the row index (Swizzle<2,5,2>) = TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+// descriptor layout type SWIZZLE_128B_BASE32B (1).  LBO = stride between 32-element MN groups, SBO = stride
+// between 4-row K groups (512 B); one K=8 MMA consumes two K groups.
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // stride between 32-element MN groups
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride between 8-row K groups
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -825,7 +881,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         cuuint32_t box[2] = {32, (cuuint32_t)WG_KP};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = g_encode_tiled(&p.amap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)dy, dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r);
@@ -840,7 +896,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         int upper[2] = {g.pad - (g.KW - 1), g.pad - (g.KH - 1)};
         cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
         CUresult r = g_encode_im2col(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, 32, WG_KP, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeIm2col(x for wgrad) failed: %d", (int)r);

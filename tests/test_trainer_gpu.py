@@ -50,8 +50,9 @@ def test_iteration_matches_oracle_and_golden(case, tc):
         xf = tr.ops.nhwc_to_nchw(tr._last_fw[d0]['x_fake'][i], 3).cpu()
         mae = (xf - orc.x_fake_gen[d0][i].detach()).abs().mean().item()
         assert mae < (2e-4 if tc == 0 else 3e-3), ('pixel MAE', i, mae)
-    wg, wp = compare_with_oracle(tr, orc, hp, rtol_loss=1e-3, grad_rel_l2=(3e-2 if tc == 0 else 1e-1),
-                                 flip_frac=(0.03 if tc == 0 else 0.12))
+    wg, wp = compare_with_oracle(tr, orc, hp, rtol_loss=1e-3, grad_rel_l2=(3e-2 if tc == 0 else 5e-2),
+                                 flip_frac=(0.03 if tc == 0 else 0.15), min_cos=(0.999 if tc == 0 else 0.9),
+                                 shallow_only=(tc == 1))
     print('%s tc=%d: worst generator grad relL2 %.2e' % (case, tc, wg))
 
 
