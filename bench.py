@@ -102,7 +102,7 @@ def cpu_oracle_rate(workload, steps, warmup):
     import council_oracle as co
     hp, n, b, size, it = load_hp(workload)
     hp['batch_size'] = 1
-    cores = min(os.cpu_count() or 1, int(os.environ.get('COUNCIL_CPU_THREADS', '32')))
+    cores = min(os.cpu_count() or 1, int(os.environ.get('COUNCIL_CPU_THREADS', '8')))  # measured on the 128-core box: 8 threads 2.07 s, 32 threads 2.78 s, 128 threads > 200 s (glasses 128x128)
     torch.set_num_threads(cores)
     states = co.synth_all_states(hp, seed=7)
     tr = co.OracleTrainer(hp, states)

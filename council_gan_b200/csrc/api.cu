@@ -6,7 +6,7 @@ namespace cg {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-int g_tc_mode = 1;
+int g_tc_mode = 7;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -53,7 +53,7 @@ extern "C" int cg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 extern "C" int cg_set_tensor_core_mode(int mode) {
     int prev = g_tc_mode;
-    g_tc_mode = mode;
+    g_tc_mode = mode == 1 ? 7 : mode;  // 1 = everything; otherwise a bit mask: 1 forward, 2 data gradient, 4 weight gradient
     return prev;
 }
 
@@ -65,10 +65,10 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     size_t need = 0;
     if (which == 1) {
         if (g->ups) need = (size_t)g->G * g->B * d.Hin * d.Win * g->Cin * sizeof(float);
-        if (g_tc_mode && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }
+        if ((g_tc_mode & 2) && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }
     }
     if (which == 2) {
-        size_t a = (g_tc_mode && tc_wgrad_supported(*g)) ? tc_wgrad_ws(*g) : simt_wgrad_ws(*g);
+        size_t a = ((g_tc_mode & 4) && tc_wgrad_supported(*g)) ? tc_wgrad_ws(*g) : simt_wgrad_ws(*g);
         size_t b = colsum_ws(g->G, d.Mpix, g->Cout);
         need = a > b ? a : b;
     }
@@ -79,7 +79,7 @@ extern "C" int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w
                            float slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_tc_mode && tc_fwd_supported(*g)) return tc_conv_fwd(*g, x, w, bias, y, act, slope, ws, ws_bytes, st);
+    if ((g_tc_mode & 1) && tc_fwd_supported(*g)) return tc_conv_fwd(*g, x, w, bias, y, act, slope, ws, ws_bytes, st);
     return simt_conv_fwd(*g, x, w, bias, y, act, slope, st);
 }
 
@@ -87,7 +87,7 @@ extern "C" int cg_conv_dgrad(const cg_conv_geom* g, const float* dy, const float
                              const float* mask_src, float mask_slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_tc_mode && tc_dgrad_supported(*g)) return tc_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, ws, ws_bytes, st);
+    if ((g_tc_mode & 2) && tc_dgrad_supported(*g)) return tc_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, ws, ws_bytes, st);
     if (!g->ups) return simt_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, st);
     size_t need = cg_conv_workspace_bytes(g, 1);
     if (need > ws_bytes) {
@@ -102,7 +102,7 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
                              size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_tc_mode && tc_wgrad_supported(*g)) {
+    if ((g_tc_mode & 4) && tc_wgrad_supported(*g)) {
         if (int rc = tc_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;
     } else {
         if (int rc = simt_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int MT = (p.B * p.P * p.Q + TC_BM - 1) / TC_BM;  // pixel tiles per (group, class)
     const int NT = (p.Cout + p.bn - 1) / p.bn;
     const int tiles = p.G * p.ncls * NT * MT;
-    const int kchunks = p.Cin / p.bk;
+    const int kchunks = (p.Cin + p.bk - 1) / p.bk;  // a partial last chunk reads zero-filled channels
     const int kiters = p.KH * p.KW * kchunks;
     const int tmem_cols = 2 * p.bn < 32 ? 32 : 2 * p.bn;
 
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             mbar_expect_tx(&full_bar[stage], (uint32_t)tx_bytes);
                             tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa, kc * p.bk, w_coord, h_coord, n_coord,
                                                (uint16_t)kw, (uint16_t)kh);
-                            tma_load_2d(&p.bmap, &full_bar[stage], sb, ((kh * p.KW + kw) * kchunks + kc) * p.bk, wrow);
+                            tma_load_2d(&p.bmap, &full_bar[stage], sb, (kh * p.KW + kw) * p.Cin + kc * p.bk, wrow);
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
             }
@@ -346,12 +346,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
             if (p.n_store < 32) {
-                // image-side data gradient: 16 accumulator columns, the first n_store (8) are the image lanes
+                // narrow outputs (image-lane gradients, the 12-channel head): 16 accumulator columns, n_store stored
                 float v[32];
                 tmem_ld16(taddr, v);
                 if (valid) {
                     for (int j = 0; j < p.n_store; j += 4) {
                         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (p.bias) {
+                            const float* bp = p.bias + (long)g * p.Cout + j;
+                            o.x += __ldg(bp); o.y += __ldg(bp + 1); o.z += __ldg(bp + 2); o.w += __ldg(bp + 3);
+                        }
                         if (p.addend) {
                             float4 a = __ldg(reinterpret_cast<const float4*>(p.addend + out_off + j));
                             o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -360,6 +364,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             float4 a = __ldg(reinterpret_cast<const float4*>(p.mask_src + out_off + j));
                             o.x *= a.x > 0.f ? 1.f : p.slope; o.y *= a.y > 0.f ? 1.f : p.slope;
                             o.z *= a.z > 0.f ? 1.f : p.slope; o.w *= a.w > 0.f ? 1.f : p.slope;
+                        } else if (p.act != CG_ACT_NONE) {
+                            o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope);
+                            o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
                         }
                         *reinterpret_cast<float4*>(p.y + out_off + j) = o;
                     }
@@ -457,6 +464,13 @@ static int pick_bn(int cout) {
     if (cout % 256 == 0) return 256;
     if (cout == 128) return 128;
     if (cout == 64) return 64;
+    if (cout <= 16 && cout % 4 == 0) return 16;  // narrow outputs: 16 accumulator columns, `cout` stored
+    return 0;
+}
+// K elements per pipeline stage: 32-channel (128-byte) rows, or 8-channel (32-byte) rows for <= 16 channels
+static int pick_bk(int cin) {
+    if (cin % TC_BK == 0) return TC_BK;
+    if (cin <= 16 && cin % 4 == 0) return 8;
     return 0;
 }
 
@@ -464,7 +478,7 @@ bool tc_fwd_supported(const cg_conv_geom& g) {
     init_driver();
     if (!g_encode_tiled || !g_encode_im2col) return false;
     if (g.ups) return false;
-    if (g.Cin % TC_BK != 0 && g.Cin != 8) return false;
+    if (pick_bk(g.Cin) == 0) return false;
     if (pick_bn(g.Cout) == 0) return false;
     if (g.pad > 120 || g.KH > 120) return false;
     if ((long)g.B * g.Ho * g.Wo < TC_BM) return false;  // tiny maps: the SIMT kernel is fine
@@ -500,7 +514,8 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
     init_driver();
     TcParams p{};
     p.bn = pick_bn(g.Cout);
-    p.bk = g.Cin % TC_BK == 0 ? TC_BK : 8;
+    p.n_store = p.bn == 16 ? g.Cout : p.bn;
+    p.bk = pick_bk(g.Cin);
     long ktot = (long)g.KH * g.KW * g.Cin;
     if (int rc = encode_weights_map(&p.bmap, w, (long)g.G * g.Cout, ktot, p.bn, p.bk)) return rc;
     long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
@@ -552,8 +567,8 @@ bool tc_dgrad_supported(const cg_conv_geom& g) {
     if (!g_encode_tiled || !g_encode_im2col) return false;
     int s = g.stride;
     if (s > 2 || g.KH % s || g.KW % s) return false;
-    if (g.Cout % TC_BK != 0) return false;                 // K dimension of the dgrad GEMM
-    if (pick_bn(g.Cin) == 0 && g.Cin != 8) return false;   // N dimension (8 = image lanes, padded to 16)
+    if (pick_bk(g.Cout) == 0) return false;   // K dimension of the dgrad GEMM
+    if (pick_bn(g.Cin) == 0) return false;    // N dimension (<= 16 image / head lanes are padded to 16)
     int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
     if (Hin % s || Win % s) return false;
     if ((long)g.B * (Hin / s) * (Win / s) < TC_BM) return false;
@@ -561,7 +576,7 @@ bool tc_dgrad_supported(const cg_conv_geom& g) {
 }
 
 size_t tc_dgrad_ws(const cg_conv_geom& g) {
-    size_t wt = (size_t)g.G * g.Cout * g.KH * g.KW * (g.Cin == 8 ? 16 : g.Cin) * sizeof(float);
+    size_t wt = (size_t)g.G * g.Cout * g.KH * g.KW * (g.Cin <= 16 ? 16 : g.Cin) * sizeof(float);
     wt = (wt + 1023) & ~(size_t)1023;
     size_t up = g.ups ? (size_t)g.G * g.B * 4 * g.H * g.W * g.Cin * sizeof(float) : 0;
     return wt + up;
@@ -578,7 +593,7 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
     const int s = g.stride, TH = g.KH / s, TW = g.KW / s, ncls = s * s;
     const int Hin = g.ups ? 2 * g.H : g.H, Win = g.ups ? 2 * g.W : g.W;
     float* wt = (float*)ws;
-    const int CinP = g.Cin == 8 ? 16 : g.Cin;
+    const int CinP = g.Cin <= 16 ? 16 : g.Cin;
     size_t wt_bytes = ((size_t)g.G * g.Cout * g.KH * g.KW * CinP * sizeof(float) + 1023) & ~(size_t)1023;
     float* d_seen = g.ups ? (float*)((uint8_t*)ws + wt_bytes) : dx;
     long total = (long)g.G * g.Cout * g.KH * g.KW * CinP;
@@ -586,18 +601,18 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
     if (int rc = check_launch("dgrad_weight_transform")) return rc;
 
     TcParams p{};
-    p.bn = g.Cin == 8 ? 16 : pick_bn(g.Cin);
-    p.n_store = g.Cin == 8 ? 8 : p.bn;
-    p.bk = TC_BK;
+    p.bn = pick_bn(g.Cin);
+    p.n_store = p.bn == 16 ? g.Cin : p.bn;
+    p.bk = pick_bk(g.Cout);
     long ktot = (long)TH * TW * g.Cout;
-    if (int rc = encode_weights_map(&p.bmap, wt, (long)g.G * ncls * CinP, ktot, p.bn)) return rc;
+    if (int rc = encode_weights_map(&p.bmap, wt, (long)g.G * ncls * CinP, ktot, p.bn, p.bk)) return rc;
     for (int c = 0; c < ncls; c++) {
         int ph = c / s, pw = c - ph * s;
         int ihf = ((ph - g.pad) % s + s) % s, iwf = ((pw - g.pad) % s + s) % s;
         int padl_h = (TH - 1) - (ihf + g.pad - ph) / s, padl_w = (TW - 1) - (iwf + g.pad - pw) / s;
         int Hc = Hin / s, Wc = Win / s;
         int up_h = Hc - g.Ho - padl_h, up_w = Wc - g.Wo - padl_w;
-        if (int rc = encode_act_map(&p.cls[c].amap, dy, (long)g.G * g.B, g.Ho, g.Wo, g.Cout, -padl_w, -padl_h, up_w, up_h, 1)) return rc;
+        if (int rc = encode_act_map(&p.cls[c].amap, dy, (long)g.G * g.B, g.Ho, g.Wo, g.Cout, -padl_w, -padl_h, up_w, up_h, 1, p.bk)) return rc;
         p.cls[c].w0 = -padl_w; p.cls[c].h0 = -padl_h;
         p.cls[c].out_h0 = ihf; p.cls[c].out_w0 = iwf;
         p.cls[c].wrow_off = c * CinP;
@@ -630,12 +645,14 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
 // atom), so no transposition is ever materialised.  The pixel range is split across CTAs (split-K) and reduced in a fixed
 // order by reduce_splits_kernel, keeping the result deterministic.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_KP = 32;  // pixels per pipeline stage (4 MMAs of K=8)
+constexpr int WG_KP = 32;      // pixels per pipeline stage (4 MMAs of K=8 per tap)
+constexpr int WG_NCOLS = 256;  // accumulator columns per TMEM stage = taps-per-unit * bn
 
 struct WgParams {
     CUtensorMap amap;  // dy  [G*Mpix][Cout]  2-D, box 32 x KP
     CUtensorMap bmap;  // x   im2col, box 32 channels x KP pixels
     int G, xg_images, B, P, Q, Cin, Cout, KH, KW, stride, pad, bn, splits, stages;
+    int T;             // filter taps accumulated per work unit (they share the dy tile): T * bn <= 256
     long Mpix, chunk;  // pixels per group; pixels per split (multiple of WG_KP)
     float* out;        // [splits][G][Cout][KH*KW][Cin]
 };
@@ -661,8 +678,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int box_bytes = WG_KP * 128;
     const int a_bytes = 4 * box_bytes;
-    const int nb = p.bn / 32;
-    const int b_bytes = nb * box_bytes;
+    const int nb = p.bn / 32;                     // 32-channel boxes per tap
+    const int b_bytes = (WG_NCOLS / 32) * box_bytes;
     const int stage_bytes = a_bytes + b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
@@ -671,10 +688,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int taps = p.KH * p.KW;
+    const int TG = (taps + p.T - 1) / p.T;        // tap groups
     const int COT = (p.Cout + 127) / 128;
     const int CIT = p.Cin / p.bn;
-    const int units = p.G * COT * p.splits * CIT * taps;
-    const int tmem_cols = 2 * p.bn < 32 ? 32 : 2 * p.bn;
+    const int units = p.G * COT * p.splits * CIT * TG;
+    const int tmem_cols = 2 * WG_NCOLS;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.amap);
@@ -701,9 +719,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // unit -> (g, cot, split, cit, tap), tap fastest so CTAs running together share the dy tile in L2
-    auto decode = [&](int u, int& g, int& cot, int& sp, int& cit, int& tap) {
-        tap = u % taps; u /= taps;
+    // unit -> (g, cot, split, cit, tap group), tap group fastest so CTAs running together share the dy tile in L2
+    auto decode = [&](int u, int& g, int& cot, int& sp, int& cit, int& tg) {
+        tg = u % TG; u /= TG;
         cit = u % CIT; u /= CIT;
         sp = u % p.splits; u /= p.splits;
         cot = u % COT;
@@ -711,30 +729,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                int g, cot, sp, cit, tap;
-                decode(u, g, cot, sp, cit, tap);
-                const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                const long mbeg = (long)sp * p.chunk;
-                const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
-                for (long m = mbeg; m < mend; m += WG_KP) {
-                    int img = (int)(m / (p.P * p.Q));
-                    int rem = (int)(m - (long)img * p.P * p.Q);
-                    int pp = rem / p.Q, qq = rem - pp * p.Q;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    for (int j = 0; j < 4; j++)
-                        tma_load_2d(&p.amap, &full_bar[stage], sa + j * box_bytes, cot * 128 + j * 32, (int)((long)g * p.Mpix + m));
-                    for (int j = 0; j < nb; j++)
-                        tma_load_im2col_4d(&p.bmap, &full_bar[stage], sb + j * box_bytes, cit * p.bn + j * 32, -p.pad + qq * p.stride,
-                                           -p.pad + pp * p.stride, g * p.xg_images + img, (uint16_t)kw, (uint16_t)kh);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
+        // ===================== TMA producer: the whole warp issues, one box per lane =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int g, cot, sp, cit, tg;
+            decode(u, g, cot, sp, cit, tg);
+            const int tap0 = tg * p.T;
+            const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
+            const long mbeg = (long)sp * p.chunk;
+            const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
+            // lane roles: 0..3 -> dy boxes; 4..4+tcount*nb -> x boxes (tap t = q / nb, channel box j = q % nb)
+            const int q = lane - 4;
+            const bool is_a = lane < 4;
+            const bool is_b = q >= 0 && q < tcount * nb;
+            const int bt = is_b ? q / nb : 0, bj = is_b ? q - bt * nb : 0;
+            const int tap = tap0 + bt;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const uint32_t tx = (uint32_t)((4 + tcount * nb) * box_bytes);
+            for (long m = mbeg; m < mend; m += WG_KP) {
+                int img = (int)(m / (p.P * p.Q));
+                int rem = (int)(m - (long)img * p.P * p.Q);
+                int pp = rem / p.Q, qq = rem - pp * p.Q;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                if (lane == 0) mbar_expect_tx(&full_bar[stage], tx);
+                __syncwarp();
+                if (is_a)
+                    tma_load_2d(&p.amap, &full_bar[stage], sa + lane * box_bytes, cot * 128 + lane * 32, (int)((long)g * p.Mpix + m));
+                if (is_b)
+                    tma_load_im2col_4d(&p.bmap, &full_bar[stage], sb + q * box_bytes, cit * p.bn + bj * 32, -p.pad + qq * p.stride,
+                                       -p.pad + pp * p.stride, g * p.xg_images + img, (uint16_t)kw, (uint16_t)kh);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -746,27 +773,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                int g, cot, sp, cit, tap;
-                decode(u, g, cot, sp, cit, tap);
+                int g, cot, sp, cit, tg;
+                decode(u, g, cot, sp, cit, tg);
+                const int tap0 = tg * p.T;
+                const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
                 const long mbeg = (long)sp * p.chunk;
                 const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
-                uint32_t first = 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_NCOLS);
+                uint32_t accum = 0;
                 for (long m = mbeg; m < mend; m += WG_KP) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     uint32_t sb = sa + a_bytes;
                     uint64_t adesc = make_mnmajor_sw128_desc(sa, box_bytes);
-                    uint64_t bdesc = make_mnmajor_sw128_desc(sb, box_bytes);
 #pragma unroll
                     for (int kk = 0; kk < WG_KP / 8; kk++) {
-                        // next 8 pixels = next 1024-byte K atom: +64 in the 16-byte address field
-                        umma_tf32(d_tmem, adesc + (uint64_t)(kk * 64), bdesc + (uint64_t)(kk * 64), idesc, (first && kk == 0) ? 0u : 1u);
+                        // next 8 pixels = next two 512-byte K atoms: +1024 B = +64 in the 16-byte address field
+                        for (int t = 0; t < tcount; t++) {
+                            uint64_t bdesc = make_mnmajor_sw128_desc(sb + t * nb * box_bytes, box_bytes);
+                            umma_tf32(d_tmem + (uint32_t)(t * p.bn), adesc + (uint64_t)(kk * 64), bdesc + (uint64_t)(kk * 64), idesc,
+                                      (accum | kk) ? 1u : 0u);
+                        }
                     }
-                    first = 0;
+                    accum = 1;
                     umma_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -781,21 +813,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
         uint32_t acc_phase = 0;
         const long ktot = (long)taps * p.Cin;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            int g, cot, sp, cit, tap;
-            decode(u, g, cot, sp, cit, tap);
+            int g, cot, sp, cit, tg;
+            decode(u, g, cot, sp, cit, tg);
+            const int tap0 = tg * p.T;
+            const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int co = cot * 128 + row;
             const bool valid = co < p.Cout;
-            float* op = p.out + (((long)sp * p.G + g) * p.Cout + co) * ktot + (long)tap * p.Cin + cit * p.bn;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
-                if (valid) {
-                    float4* yp = reinterpret_cast<float4*>(op + c0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * WG_NCOLS);
+            for (int t = 0; t < tcount; t++) {
+                float* op = p.out + (((long)sp * p.G + g) * p.Cout + co) * ktot + (long)(tap0 + t) * p.Cin + cit * p.bn;
+                for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(t * p.bn + c0), v);
+                    if (valid) {
+                        float4* yp = reinterpret_cast<float4*>(op + c0);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; j++) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 }
             }
             tc_fence_before();
@@ -833,7 +869,9 @@ static int wg_bn(int cin) {
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
     int bn = wg_bn(g.Cin);
-    long units = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * g.KH * g.KW;
+    int T = WG_NCOLS / bn;
+    if (T > g.KH * g.KW) T = g.KH * g.KW;
+    long units = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
     init_driver();
     long want = (2L * g_sm_count + units - 1) / units;
     long maxs = Mpix / (WG_KP * 8);  // at least 8 stages of work per split
@@ -850,7 +888,7 @@ bool tc_wgrad_supported(const cg_conv_geom& g) {
     if (!g_encode_tiled || !g_encode_im2col) return false;
     if (g.ups) return false;
     if (wg_bn(g.Cin) == 0) return false;
-    if (g.Cout % 32 != 0) return false;
+    if (g.Cout % 4 != 0) return false;
     long Mpix = (long)g.B * g.Ho * g.Wo;
     if (Mpix % WG_KP != 0 || Mpix < 256) return false;
     if (g.pad > 120 || g.KH > 120) return false;
@@ -908,9 +946,10 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     p.B = g.B; p.P = g.Ho; p.Q = g.Wo; p.Cin = g.Cin; p.Cout = g.Cout; p.KH = g.KH; p.KW = g.KW;
     p.stride = g.stride; p.pad = g.pad;
     p.out = p.splits == 1 ? dw : (float*)ws;
-    int stage_bytes = WG_KP * 128 * (4 + p.bn / 32);
+    p.T = WG_NCOLS / p.bn;
+    if (p.T > g.KH * g.KW) p.T = g.KH * g.KW;
+    int stage_bytes = WG_KP * 128 * (4 + WG_NCOLS / 32);
     int stages = (200 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
     static bool attr_set = false;
@@ -922,7 +961,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         }
         attr_set = true;
     }
-    long units = (long)g.G * ((g.Cout + 127) / 128) * p.splits * (g.Cin / p.bn) * g.KH * g.KW;
+    long units = (long)g.G * ((g.Cout + 127) / 128) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
     int grid = (int)(units < g_sm_count ? units : g_sm_count);
     wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
     if (int rc = check_launch("wgrad_tc_kernel")) return rc;

@@ -54,8 +54,9 @@ typedef struct {
 const char* cg_last_error(void);
 /* Library / device introspection: returns the SM count of the current device (>0) or a cg_status. */
 int cg_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* 0 = SIMT fp32 reference kernels only, 1 = tcgen05 TF32 tensor-core path where a layer qualifies.
- * Returns the previous value.  Default 1. */
+/* 0 = SIMT fp32 kernels only; 1 (default) = tcgen05 TF32 tensor-core kernels wherever a layer qualifies;
+ * other values are a bit mask for bring-up: 2 = data gradient only, 4 = weight gradient only, ...
+ * (internally 1 forward | 2 dgrad | 4 wgrad).  Returns the previous mask. */
 int cg_set_tensor_core_mode(int mode);
 /* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
 uint64_t cg_launch_count(void);

@@ -55,6 +55,14 @@ CONV_CASES = [
     ('mlp_linear', 2, 1, 3, 1, 1, 64, 256, 1, 1, 0, False),
     ('mlp_linear_big', 2, 2, 3, 1, 1, 256, 5888, 1, 1, 0, False),
     ('odd_sizes', 1, 1, 1, 10, 14, 8, 20, 3, 1, 1, False),
+    # shapes that qualify for the tcgen05 path (>= 128 output pixels per member)
+    ('tc_res_3x3_256', 2, 2, 2, 16, 16, 256, 256, 3, 1, 1, False),
+    ('tc_down_4x4s2_64_128', 2, 2, 2, 32, 32, 64, 128, 4, 2, 1, False),
+    ('tc_down_4x4s2_256_512', 2, 2, 3, 16, 16, 256, 512, 4, 2, 1, False),
+    ('tc_up_3x3_128_64', 2, 2, 1, 32, 32, 128, 64, 3, 1, 1, False),
+    ('tc_dc_1x1_512_512', 3, 3, 4, 8, 8, 512, 512, 1, 1, 0, False),
+    ('tc_shared_input', 3, 1, 2, 16, 16, 64, 64, 3, 1, 1, False),
+    ('tc_partial_tiles', 2, 2, 3, 12, 20, 64, 128, 3, 1, 1, False),
 ]
 
 
@@ -68,9 +76,14 @@ def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
         x = rnd(Gx, B, H, W, Cin, seed=1)
         w = rnd(G, Cout, K, K, Cin, seed=2, scale=0.1)
         b = rnd(G, Cout, seed=3)
+        pre = ref.conv_fwd(d(x), d(w), d(b), stride, pad, ups=ups, act=0)
+        pre_mag = pre.abs().max().item()
         for act in (0, 1, 2, 3):
             y = ops.conv_fwd(x, w, b, stride, pad, ups=ups, act=act, slope=0.2)
-            check(y, ref.conv_fwd(d(x), d(w), d(b), stride, pad, ups=ups, act=act, slope=0.2), tol, name + ' fwd act%d' % act)
+            want = ref.conv_fwd(d(x), d(w), d(b), stride, pad, ups=ups, act=act, slope=0.2)
+            # every activation is 1-Lipschitz: the error budget is that of the pre-activation
+            err = (y.double() - want).abs().max().item()
+            assert err <= tol * pre_mag + 1e-7, '%s fwd act%d: max err %.3e vs pre-activation magnitude %.3e' % (name, act, err, pre_mag)
         y = ops.conv_fwd(x, w, None, stride, pad, ups=ups)
         check(y, ref.conv_fwd(d(x), d(w), None, stride, pad, ups=ups), tol, name + ' fwd nobias')
         dy = rnd(*y.shape, seed=4)

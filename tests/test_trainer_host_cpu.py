@@ -98,7 +98,7 @@ def compare_with_oracle(tr, orc, hp, rtol_loss, grad_rel_l2, flip_frac, min_cos=
                     if key.startswith('enc_style'):
                         assert torch.equal(sd[key].cpu().to(ref.dtype), ref), key  # never stepped
                         continue
-                    deep = shallow_only and fam == 'gen' and not key.startswith('dec.model.9')
+                    deep = shallow_only and fam == 'gen'
                     diff = (sd[key].cpu().to(ref.dtype) - ref).abs()
                     worst_p = max(worst_p, diff.max().item())
                     frac = (diff > 0.5 * hp['lr']).double().mean().item()
