@@ -509,6 +509,37 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
     for (int k = 0; k < nchunks; k++) s += part[(long)k * GC + i];
     out[i] = s;
 }
+// float4-vectorised variant for C % 4 == 0, C/4 dividing 256: lanes = C/4 threads across channels, 256/lanes row lanes
+__global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __restrict__ dy, float* __restrict__ part, long rows, int C) {
+    __shared__ float4 sm[256];
+    const int g = blockIdx.y, chunk = blockIdx.x;
+    const int lanes = C >> 2, rowl = 256 / lanes;
+    const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+    const long r0 = (long)chunk * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+    const float* base = dy + (long)g * rows * C + lane * 4;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    long r = r0 + rl;
+    for (; r + rowl < r1; r += 2 * rowl) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(base + r * C));
+        float4 b = __ldg(reinterpret_cast<const float4*>(base + (r + rowl) * C));
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+    }
+    if (r < r1) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(base + r * C));
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+    }
+    s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+    sm[threadIdx.x] = s0;
+    __syncthreads();
+    if (rl == 0) {
+        for (int k = 1; k < rowl; k++) {
+            float4 a = sm[k * lanes + lane];
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+        *reinterpret_cast<float4*>(part + ((long)chunk * gridDim.y + g) * C + lane * 4) = s0;
+    }
+}
 size_t colsum_ws(int G, long rows, int C) { return (size_t)cdiv(rows, CS_ROWS) * G * C * sizeof(float); }
 int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
     size_t need = colsum_ws(G, rows, C);
@@ -517,7 +548,10 @@ int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t
         return CG_ERR_WORKSPACE;
     }
     int nchunks = cdiv(rows, CS_ROWS);
-    colsum_partial_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, nchunks);
+    if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
+        colsum_partial_v4_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C);
+    else
+        colsum_partial_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, nchunks);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
     colsum_final_kernel<<<cdiv((long)G * C, 256), 256, 0, st>>>((const float*)ws, db, G * C, nchunks);

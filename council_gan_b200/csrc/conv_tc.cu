@@ -377,9 +377,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 if (valid) {
                     if (p.bias) {
-                        const float* bp = p.bias + (long)g * p.Cout + nt * p.bn + c0;
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] += __ldg(bp + j);
+                        for (int j = 0; j < 8; j++) {
+                            float4 a = __ldg(bp + j);
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        }
                     }
                     if (p.addend) {
                         const float4* ap = reinterpret_cast<const float4*>(p.addend + out_off + c0);
@@ -871,14 +874,23 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     int bn = wg_bn(g.Cin);
     int T = WG_NCOLS / bn;
     if (T > g.KH * g.KW) T = g.KH * g.KW;
-    long units = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
+    long base = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
     init_driver();
-    long want = (2L * g_sm_count + units - 1) / units;
-    long maxs = Mpix / (WG_KP * 8);  // at least 8 stages of work per split
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    long maxs = Mpix / (WG_KP * 16);  // at least 16 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
-    splits = (int)(want < maxs ? want : maxs);
-    if (splits < 1) splits = 1;
-    if (splits > 32) splits = 32;
+    if (maxs > 32) maxs = 32;
+    // pick the split count whose unit count fills whole waves best (persistent grid = #SMs), preferring >= 3 waves
+    int best = 1;
+    double best_score = -1.0;
+    for (int s = 1; s <= maxs; s++) {
+        long units = base * s;
+        long waves = (units + sms - 1) / sms;
+        double eff = (double)units / (double)(waves * sms);
+        double score = eff - 0.01 * s - (waves < 3 ? 0.15 * (3 - waves) : 0.0);
+        if (score > best_score) { best_score = score; best = s; }
+    }
+    splits = best;
     chunk = ((Mpix + splits - 1) / splits + WG_KP - 1) / WG_KP * WG_KP;
     splits = (int)((Mpix + chunk - 1) / chunk);
 }

@@ -326,7 +326,8 @@ class CouncilGen(_StackedNet):
         the following convolution is a plain 3x3 on the materialised tensor (TMA im2col cannot halve indices)."""
         ops = self.ops
         w, b = self._w(s, sl)
-        y = ops.conv_fwd(x, w, b, s.stride, s.pad)
+        # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
+        y = ops.conv_fwd(x, w, None, s.stride, s.pad)
         mean, rstd = ops.in_stats(y)
         off = self.adain_off.get(s.key, 0)
         z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
