@@ -26,6 +26,77 @@ int validate_geom(const cg_conv_geom& g) {
     return CG_OK;
 }
 
+// ---- patch path for the image-side layers (Cin <= 8: 3/4-lane images, the 8-lane council-D pair) -----------
+// TMA im2col moves 16..32 bytes per pixel-tap for these layers and is request-bound, so their (tiny) input is
+// expanded once into an explicit patch matrix P[pixel][KH*KW*Cin padded to 32k] and the layer runs as a 1x1
+// convolution on the tensor path.  P is 96..224 floats per pixel -- small next to the 64-channel output.
+static bool patch_path(const cg_conv_geom& g) {
+    if (!g_tc_mode || g.ups || g.Cin > 8 || g.Cout % 32 != 0) return false;
+    int k2p = (g.KH * g.KW * g.Cin + 31) / 32 * 32;
+    if (k2p > 256) return false;
+    long mpix = (long)g.B * g.Ho * g.Wo;
+    return mpix >= 256 && mpix % 32 == 0;
+}
+static cg_conv_geom patch_geom(const cg_conv_geom& g) {
+    cg_conv_geom p = g;
+    p.H = g.Ho; p.W = g.Wo; p.Cin = (g.KH * g.KW * g.Cin + 31) / 32 * 32;
+    p.KH = p.KW = 1; p.stride = 1; p.pad = 0; p.ups = 0;
+    return p;
+}
+static size_t patch_bytes(const cg_conv_geom& g) {
+    cg_conv_geom p = patch_geom(g);
+    return ((size_t)(g.x_groups == 1 ? 1 : g.G) * g.B * g.Ho * g.Wo * p.Cin * sizeof(float) + 1023) & ~(size_t)1023;
+}
+static size_t patch_w_bytes(const cg_conv_geom& g) {
+    cg_conv_geom p = patch_geom(g);
+    return ((size_t)g.G * g.Cout * p.Cin * sizeof(float) + 1023) & ~(size_t)1023;
+}
+
+__global__ void im2col_small_kernel(const float* __restrict__ x, float* __restrict__ P, long total4, int H, int W, int Cin, int Ho, int Wo,
+                                    int KH, int KW, int stride, int pad, int K2, int K2p) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 slot of P
+    if (i >= total4) return;
+    int slots = K2p >> 2;
+    int slot = (int)(i % slots);
+    long pix = i / slots;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = slot * 4;
+    if (k < K2) {
+        int tap = k / Cin, ci = k - tap * Cin;
+        int kh = tap / KW, kw = tap - kh * KW;
+        int ow = (int)(pix % Wo);
+        long t = pix / Wo;
+        int oh = (int)(t % Ho);
+        long n = t / Ho;
+        int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(reinterpret_cast<const float4*>(x + ((n * H + ih) * W + iw) * Cin + ci));
+    }
+    reinterpret_cast<float4*>(P)[i] = v;
+}
+// rows of K2 floats <-> rows of K2p floats (zero padded); dir 0: pad (w -> wp), 1: unpad (dwp -> dw)
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long rows, int K2, int K2p, int dir) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dir == 0) {
+        if (i >= rows * K2p) return;
+        long r = i / K2p;
+        int k = (int)(i - r * K2p);
+        dst[i] = k < K2 ? __ldg(src + r * K2 + k) : 0.f;
+    } else {
+        if (i >= rows * K2) return;
+        long r = i / K2;
+        int k = (int)(i - r * K2);
+        dst[i] = __ldg(src + r * K2p + k);
+    }
+}
+static int run_im2col(const cg_conv_geom& g, const float* x, float* P, cudaStream_t st) {
+    cg_conv_geom p = patch_geom(g);
+    long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
+    long total4 = nimg * g.Ho * g.Wo * (p.Cin / 4);
+    im2col_small_kernel<<<cdiv(total4, 256), 256, 0, st>>>(x, P, total4, g.H, g.W, g.Cin, g.Ho, g.Wo, g.KH, g.KW, g.stride, g.pad,
+                                                          g.KH * g.KW * g.Cin, p.Cin);
+    return check_launch("im2col_small");
+}
+
 }  // namespace cg
 
 using namespace cg;
@@ -63,6 +134,14 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     if (!g) return 0;
     ConvDims d = conv_dims(*g);
     size_t need = 0;
+    if (which != 1 && patch_path(*g)) {
+        cg_conv_geom p = patch_geom(*g);
+        ConvDims dp = conv_dims(p);
+        size_t inner = which == 2 ? tc_wgrad_ws(p) : 0;
+        size_t cs = which == 2 ? colsum_ws(g->G, dp.Mpix, g->Cout) : 0;
+        if (cs > inner) inner = cs;
+        return patch_bytes(*g) + 2 * patch_w_bytes(*g) + inner;
+    }
     if (which == 1) {
         if (g->ups) need = (size_t)g->G * g->B * d.Hin * d.Win * g->Cin * sizeof(float);
         if ((g_tc_mode & 2) && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }
@@ -79,6 +158,21 @@ extern "C" int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w
                            float slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((g_tc_mode & 1) && patch_path(*g)) {
+        size_t need = cg_conv_workspace_bytes(g, 0);
+        if (need > ws_bytes) {
+            set_error("conv_fwd(patch path): workspace %zu < %zu bytes", ws_bytes, need);
+            return CG_ERR_WORKSPACE;
+        }
+        cg_conv_geom p = patch_geom(*g);
+        float* P = (float*)ws;
+        float* wp = (float*)((uint8_t*)ws + patch_bytes(*g));
+        if (int rc = run_im2col(*g, x, P, st)) return rc;
+        long rows = (long)g->G * g->Cout;
+        pad_rows_kernel<<<cdiv(rows * p.Cin, 256), 256, 0, st>>>(w, wp, rows, g->KH * g->KW * g->Cin, p.Cin, 0);
+        if (int rc = check_launch("pad_rows")) return rc;
+        return tc_conv_fwd(p, P, wp, bias, y, act, slope, nullptr, 0, st);
+    }
     if ((g_tc_mode & 1) && tc_fwd_supported(*g)) return tc_conv_fwd(*g, x, w, bias, y, act, slope, ws, ws_bytes, st);
     return simt_conv_fwd(*g, x, w, bias, y, act, slope, st);
 }
@@ -102,6 +196,27 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
                              size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((g_tc_mode & 4) && patch_path(*g)) {
+        size_t need = cg_conv_workspace_bytes(g, 2);
+        if (need > ws_bytes) {
+            set_error("conv_wgrad(patch path): workspace %zu < %zu bytes", ws_bytes, need);
+            return CG_ERR_WORKSPACE;
+        }
+        cg_conv_geom p = patch_geom(*g);
+        ConvDims dp = conv_dims(p);
+        float* P = (float*)ws;
+        float* dwp = (float*)((uint8_t*)ws + patch_bytes(*g));
+        uint8_t* inner = (uint8_t*)ws + patch_bytes(*g) + 2 * patch_w_bytes(*g);
+        size_t inner_bytes = ws_bytes - (size_t)(inner - (uint8_t*)ws);
+        if (int rc = run_im2col(*g, x, P, st)) return rc;
+        if (int rc = tc_conv_wgrad(p, P, dy, dwp, inner, inner_bytes, st)) return rc;
+        long rows = (long)g->G * g->Cout;
+        int K2 = g->KH * g->KW * g->Cin;
+        pad_rows_kernel<<<cdiv(rows * K2, 256), 256, 0, st>>>(dwp, dw, rows, K2, p.Cin, 1);
+        if (int rc = check_launch("unpad_rows")) return rc;
+        if (db) return colsum(dy, db, g->G, dp.Mpix, g->Cout, inner, inner_bytes, st);
+        return CG_OK;
+    }
     if ((g_tc_mode & 4) && tc_wgrad_supported(*g)) {
         if (int rc = tc_conv_wgrad(*g, x, dy, dw, ws, ws_bytes, st)) return rc;
     } else {

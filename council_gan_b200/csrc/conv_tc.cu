@@ -863,9 +863,7 @@ __global__ void reduce_splits_tc_kernel(const float* __restrict__ part, float* _
 
 static int wg_bn(int cin) {
     if (cin % 256 == 0) return 256;
-    if (cin == 128) return 128;
-    if (cin == 64) return 64;
-    if (cin == 32) return 32;
+    if (cin % 32 == 0 && cin < 256) return cin;  // 32 .. 224: one N tile
     return 0;
 }
 
@@ -879,7 +877,7 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     long maxs = Mpix / (WG_KP * 16);  // at least 16 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
-    if (maxs > 32) maxs = 32;
+    if (maxs > 64) maxs = 64;
     // pick the split count whose unit count fills whole waves best (persistent grid = #SMs), preferring >= 3 waves
     int best = 1;
     double best_score = -1.0;

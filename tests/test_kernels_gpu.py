@@ -63,6 +63,10 @@ CONV_CASES = [
     ('tc_dc_1x1_512_512', 3, 3, 4, 8, 8, 512, 512, 1, 1, 0, False),
     ('tc_shared_input', 3, 1, 2, 16, 16, 64, 64, 3, 1, 1, False),
     ('tc_partial_tiles', 2, 2, 3, 12, 20, 64, 128, 3, 1, 1, False),
+    # image-side layers on the explicit-patch path (im2col -> 1x1 tensor-core GEMM)
+    ('patch_disc0_3x3_pair', 2, 2, 2, 16, 16, 8, 64, 3, 1, 1, False),
+    ('patch_dis0_4x4s2_img', 2, 2, 4, 16, 16, 4, 64, 4, 2, 1, False),
+    ('patch_enc0_7x7_shared', 3, 1, 2, 16, 16, 4, 64, 7, 1, 3, False),
 ]
 
 
