@@ -74,6 +74,7 @@ int pool2x2_sum(const float* d_up, float* dx, const float* addend, const float* 
 bool tc_fwd_supported(const cg_conv_geom& g);
 int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y,
                 int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_fwd_ws(const cg_conv_geom& g);
 bool tc_dgrad_supported(const cg_conv_geom& g);
 size_t tc_dgrad_ws(const cg_conv_geom& g);
 int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float* dx, const float* addend,

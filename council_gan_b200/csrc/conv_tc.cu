@@ -196,6 +196,7 @@ struct TcParams {
     int Cin, Cout, KH, KW, stride;  // KH,KW: taps per class
     int bn;                         // N tile
     int bk;                         // K elements per stage: 32 (128-byte swizzled rows) or 8 (32-byte rows, Cin = 8)
+    int cps;                        // K chunks per pipeline stage (small-N layers batch several: the MMA issue loop is latency bound)
     int n_store;                    // output channels actually stored per N tile (== bn except the 8-lane image gradient)
     int out_H, out_W, out_sh, out_sw;  // full output spatial size and class strides
     int w_rows_per_group;           // weight rows per group (ncls * Cout for dgrad classes)
@@ -204,14 +205,15 @@ struct TcParams {
     int stages;
 };
 
+template <int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = TC_BM * p.bk * 4;
-    const int b_bytes = ((p.bn * p.bk * 4) + 1023) & ~1023;
-    const int stage_bytes = a_bytes + b_bytes;
-    const int tx_bytes = a_bytes + p.bn * p.bk * 4;
+    const int a_bytes = TC_BM * BK * 4;                       // one K chunk of A
+    const int b_bytes = ((p.bn * BK * 4) + 1023) & ~1023;    // one K chunk of B (slot size)
+    const int stage_bytes = p.cps * (a_bytes + b_bytes);       // [A_0..A_cps-1][B_0..B_cps-1]
+    const int tx_chunk = a_bytes + p.bn * BK * 4;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tfull_bar = empty_bar + p.stages;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int MT = (p.B * p.P * p.Q + TC_BM - 1) / TC_BM;  // pixel tiles per (group, class)
     const int NT = (p.Cout + p.bn - 1) / p.bn;
     const int tiles = p.G * p.ncls * NT * MT;
-    const int kchunks = (p.Cin + p.bk - 1) / p.bk;  // a partial last chunk reads zero-filled channels
+    const int kchunks = (p.Cin + BK - 1) / BK;  // a partial last chunk reads zero-filled channels
     const int kiters = p.KH * p.KW * kchunks;
     const int tmem_cols = 2 * p.bn < 32 ? 32 : 2 * p.bn;
 
@@ -272,24 +274,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 int w_coord = cl.w0 + qq * p.stride;
                 int h_coord = cl.h0 + pp * p.stride;
                 int wrow = g * p.w_rows_per_group + cl.wrow_off + nt * p.bn;
-                for (int kh = 0; kh < p.KH; kh++)
-                    for (int kw = 0; kw < p.KW; kw++)
-                        for (int kc = 0; kc < kchunks; kc++) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                            uint8_t* sb = sa + a_bytes;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)tx_bytes);
-                            tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa, kc * p.bk, w_coord, h_coord, n_coord,
-                                               (uint16_t)kw, (uint16_t)kh);
-                            tma_load_2d(&p.bmap, &full_bar[stage], sb, (kh * p.KW + kw) * p.Cin + kc * p.bk, wrow);
-                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                        }
+                int kh = 0, kw = 0, kc = 0;
+                for (int k0 = 0; k0 < kiters; k0 += p.cps) {
+                    const int n = kiters - k0 < p.cps ? kiters - k0 : p.cps;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + p.cps * a_bytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)(n * tx_chunk));
+                    for (int j = 0; j < n; j++) {
+                        tma_load_im2col_4d(&cl.amap, &full_bar[stage], sa + j * a_bytes, kc * BK, w_coord, h_coord, n_coord, (uint16_t)kw,
+                                           (uint16_t)kh);
+                        tma_load_2d(&p.bmap, &full_bar[stage], sb + j * b_bytes, (kh * p.KW + kw) * p.Cin + kc * BK, wrow);
+                        if (++kc == kchunks) { kc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(p.bn);
+            // descriptor without the start address (same for every chunk of this launch)
+            const uint64_t desc_hi = (BK == 32 ? make_kmajor_sw128_desc(0) : make_kmajor_sw32_desc(0));
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -298,17 +305,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
-                for (int k = 0; k < kiters; k++) {
+                for (int k0 = 0; k0 < kiters; k0 += p.cps) {
+                    const int n = kiters - k0 < p.cps ? kiters - k0 : p.cps;
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    uint32_t sb = sa + a_bytes;
-                    uint64_t adesc = p.bk == 32 ? make_kmajor_sw128_desc(sa) : make_kmajor_sw32_desc(sa);
-                    uint64_t bdesc = p.bk == 32 ? make_kmajor_sw128_desc(sb) : make_kmajor_sw32_desc(sb);
-                    const int nmma = p.bk / 8;
-                    for (int kk = 0; kk < nmma; kk++) {
-                        // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzled row: +2 in the 16-byte address field
-                        umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + p.cps * a_bytes;
+                    for (int j = 0; j < n; j++) {
+                        const uint64_t adesc = desc_hi | (uint64_t)(((sa + j * a_bytes) & 0x3FFFF) >> 4);
+                        const uint64_t bdesc = desc_hi | (uint64_t)(((sb + j * b_bytes) & 0x3FFFF) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; kk++) {
+                            // advance 8 tf32 (32 bytes) along K inside the swizzled row: +2 in the 16-byte address field
+                            umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k0 | j | kk) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -323,7 +333,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int row = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const long PQ = (long)p.P * p.Q;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             int mt = t % MT;
             int r = t / MT;
@@ -334,12 +343,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const TcClass& cl = p.cls[c];
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            long m = (long)mt * TC_BM + row;
-            bool valid = m < (long)p.B * PQ;
+            const int m = mt * TC_BM + row;      // < 2^31: B*P*Q pixels per member
+            const int pq = p.P * p.Q;
+            bool valid = m < p.B * pq;
             long out_off = 0;
             if (valid) {
-                int img = (int)(m / PQ);
-                int rem = (int)(m - (long)img * PQ);
+                int img = m / pq;
+                int rem = m - img * pq;
                 int pp = rem / p.Q, qq = rem - pp * p.Q;
                 long pix = ((long)(g * p.B + img) * p.out_H + (pp * p.out_sh + cl.out_h0)) * p.out_W + (qq * p.out_sw + cl.out_w0);
                 out_off = pix * p.Cout + nt * p.n_store;
@@ -350,7 +360,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 float v[32];
                 tmem_ld16(taddr, v);
                 if (valid) {
-                    for (int j = 0; j < p.n_store; j += 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        if (j >= p.n_store) break;
                         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         if (p.bias) {
                             const float* bp = p.bias + (long)g * p.Cout + j;
@@ -400,10 +412,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             v[4 * j] *= a.x > 0.f ? 1.f : p.slope; v[4 * j + 1] *= a.y > 0.f ? 1.f : p.slope;
                             v[4 * j + 2] *= a.z > 0.f ? 1.f : p.slope; v[4 * j + 3] *= a.w > 0.f ? 1.f : p.slope;
                         }
-                    } else if (p.act != CG_ACT_NONE) {
+                    } else if (p.act == CG_ACT_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = apply_act(v[j], p.act, p.slope);
-                    }
+                        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == CG_ACT_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+                    }  // tanh only occurs on the narrow (<= 16 channel) path; a rolled loop here would push v[] into local memory
                     float4* yp = reinterpret_cast<float4*>(p.y + out_off + c0);
 #pragma unroll
                     for (int j = 0; j < 8; j++) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -480,17 +495,25 @@ static int pick_bk(int cin) {
 bool tc_fwd_supported(const cg_conv_geom& g) {
     init_driver();
     if (!g_encode_tiled || !g_encode_im2col) return false;
-    if (g.ups) return false;
+    if (g.ups && !(g.KH == 3 && g.KW == 3 && g.stride == 1 && g.pad == 1 && g.Cin % TC_BK == 0)) return false;
     if (pick_bk(g.Cin) == 0) return false;
     if (pick_bn(g.Cout) == 0) return false;
     if (g.pad > 120 || g.KH > 120) return false;
-    if ((long)g.B * g.Ho * g.Wo < TC_BM) return false;  // tiny maps: the SIMT kernel is fine
+    if ((long)g.B * (g.ups ? g.H * g.W : g.Ho * g.Wo) < TC_BM) return false;  // tiny maps: the SIMT kernel is fine
     return true;
 }
 
 static int launch_tc(TcParams& p, cudaStream_t st) {
     int a_bytes = TC_BM * p.bk * 4, b_bytes = ((p.bn * p.bk * 4) + 1023) & ~1023;
-    int stage_bytes = a_bytes + b_bytes;
+    int chunk_bytes = a_bytes + b_bytes;
+    // several K chunks per stage when a chunk carries little tensor work (N <= 64 or 32-byte rows): the single MMA-issuing
+    // thread pays ~300 cycles of barrier / descriptor latency per stage
+    int kiters = p.KH * p.KW * ((p.Cin + p.bk - 1) / p.bk);
+    int cps = p.bn <= 128 ? 2 : 1;   // 48 KB (N=64) / 64 KB (N=128) stages, 4 / 3 deep
+    if (p.bk == 8) cps = 8;          // 6 KB chunks
+    while (cps > 1 && (cps > kiters || cps * chunk_bytes > 64 * 1024)) cps >>= 1;
+    p.cps = cps;
+    int stage_bytes = cps * chunk_bytes;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 12) stages = 12;
     if (p.n_store == 0) p.n_store = p.bn;
@@ -498,7 +521,8 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
@@ -508,8 +532,38 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     int MT = cdiv((long)p.B * p.P * p.Q, TC_BM);
     long tiles = (long)p.G * p.ncls * ((p.Cout + p.bn - 1) / p.bn) * MT;
     int grid = (int)(tiles < g_sm_count ? tiles : g_sm_count);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+    if (p.bk == 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(p);
+    else conv_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(p);
     return check_launch("conv_tc_kernel");
+}
+
+// nearest-upsample x2 followed by a 3x3 pad-1 convolution == four 2x2 convolutions on the ORIGINAL tensor, one per
+// output parity (a,b): output row 2i+a reads source rows {i-1,i} (a=0) or {i,i+1} (a=1), and the 3 filter rows
+// collapse onto those 2 source rows: a=0 -> {w0, w1+w2}, a=1 -> {w0+w1, w2} (same along columns).  2.25x fewer
+// FLOPs than convolving the materialised upsampled tensor, and the upsampled tensor never exists.
+__global__ void ups_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wc, long total, int Cout, int Cin) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // wc[g][cls][co][r][s][ci]
+    if (i >= total) return;
+    int ci = (int)(i % Cin);
+    long t = i / Cin;
+    int ss = (int)(t % 2); t /= 2;
+    int r = (int)(t % 2); t /= 2;
+    int co = (int)(t % Cout); t /= Cout;
+    int cls = (int)(t % 4);
+    int g = (int)(t / 4);
+    int a = cls >> 1, b = cls & 1;
+    // taps of the 3-wide filter that land on source offset r for parity a
+    int kh0 = a == 0 ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), kh1 = a == 0 ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+    int kw0 = b == 0 ? (ss == 0 ? 0 : 1) : (ss == 0 ? 0 : 2), kw1 = b == 0 ? (ss == 0 ? 0 : 2) : (ss == 0 ? 1 : 2);
+    const float* wp = w + ((long)g * Cout + co) * 9 * Cin + ci;
+    float acc = 0.f;
+    for (int kh = kh0; kh <= kh1; kh++)
+        for (int kw = kw0; kw <= kw1; kw++) acc += __ldg(wp + (kh * 3 + kw) * Cin);
+    wc[i] = acc;
+}
+
+size_t tc_fwd_ws(const cg_conv_geom& g) {
+    return g.ups ? (size_t)g.G * 4 * g.Cout * 4 * g.Cin * sizeof(float) : 0;
 }
 
 int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, int act, float slope, void* ws,
@@ -519,23 +573,47 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
     p.bn = pick_bn(g.Cout);
     p.n_store = p.bn == 16 ? g.Cout : p.bn;
     p.bk = pick_bk(g.Cin);
+    long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
+    p.G = g.G; p.xg_images = g.x_groups == 1 ? 0 : g.B;
+    p.B = g.B; p.Cin = g.Cin; p.Cout = g.Cout;
+    p.y = y; p.bias = bias; p.addend = nullptr; p.mask_src = nullptr; p.act = act; p.slope = slope;
+    if (g.ups) {
+        size_t need = tc_fwd_ws(g);
+        if (need > ws_bytes) {
+            set_error("conv_fwd(tc, upsample classes): workspace %zu < %zu bytes", ws_bytes, need);
+            return CG_ERR_WORKSPACE;
+        }
+        float* wc = (float*)ws;
+        long total = (long)g.G * 4 * g.Cout * 4 * g.Cin;
+        ups_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wc, total, g.Cout, g.Cin);
+        if (int rc = check_launch("ups_weight_transform")) return rc;
+        if (int rc = encode_weights_map(&p.bmap, wc, (long)g.G * 4 * g.Cout, 4L * g.Cin, p.bn, p.bk)) return rc;
+        for (int c = 0; c < 4; c++) {
+            int a = c >> 1, b = c & 1;
+            int lo_h = a == 0 ? -1 : 0, lo_w = b == 0 ? -1 : 0;  // lower corner = -(left pad); upper = right pad - (K-1), K = 2
+            int up_h = a == 0 ? -1 : 0, up_w = b == 0 ? -1 : 0;
+            if (int rc = encode_act_map(&p.cls[c].amap, x, nimg, g.H, g.W, g.Cin, lo_w, lo_h, up_w, up_h, 1, p.bk)) return rc;
+            p.cls[c].w0 = lo_w; p.cls[c].h0 = lo_h; p.cls[c].out_h0 = a; p.cls[c].out_w0 = b; p.cls[c].wrow_off = c * g.Cout;
+        }
+        p.ncls = 4;
+        p.P = g.H; p.Q = g.W; p.KH = 2; p.KW = 2; p.stride = 1;
+        p.out_H = g.Ho; p.out_W = g.Wo; p.out_sh = 2; p.out_sw = 2;
+        p.w_rows_per_group = 4 * g.Cout;
+        return launch_tc(p, st);
+    }
     long ktot = (long)g.KH * g.KW * g.Cin;
     if (int rc = encode_weights_map(&p.bmap, w, (long)g.G * g.Cout, ktot, p.bn, p.bk)) return rc;
-    long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
     if (int rc = encode_act_map(&p.cls[0].amap, x, nimg, g.H, g.W, g.Cin, -g.pad, -g.pad, g.pad - (g.KW - 1), g.pad - (g.KH - 1), g.stride,
                                 p.bk))
         return rc;
     p.cls[0].w0 = -g.pad; p.cls[0].h0 = -g.pad; p.cls[0].out_h0 = 0; p.cls[0].out_w0 = 0; p.cls[0].wrow_off = 0;
     p.ncls = 1;
-    p.G = g.G; p.xg_images = g.x_groups == 1 ? 0 : g.B;
-    p.B = g.B; p.P = g.Ho; p.Q = g.Wo;
-    p.Cin = g.Cin; p.Cout = g.Cout; p.KH = g.KH; p.KW = g.KW; p.stride = g.stride;
+    p.P = g.Ho; p.Q = g.Wo;
+    p.KH = g.KH; p.KW = g.KW; p.stride = g.stride;
     p.out_H = g.Ho; p.out_W = g.Wo; p.out_sh = 1; p.out_sw = 1;
     p.w_rows_per_group = g.Cout;
-    p.y = y; p.bias = bias; p.addend = nullptr; p.mask_src = nullptr; p.act = act; p.slope = slope;
     return launch_tc(p, st);
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // data gradient on the same kernel
@@ -648,13 +726,14 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
 // atom), so no transposition is ever materialised.  The pixel range is split across CTAs (split-K) and reduced in a fixed
 // order by reduce_splits_kernel, keeping the result deterministic.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_KP = 32;      // pixels per pipeline stage (4 MMAs of K=8 per tap)
+constexpr int WG_KP = 32;      // pixel granularity (tensor-map box rows are kp = 32 or 64)
 constexpr int WG_NCOLS = 256;  // accumulator columns per TMEM stage = taps-per-unit * bn
 
 struct WgParams {
     CUtensorMap amap;  // dy  [G*Mpix][Cout]  2-D, box 32 x KP
     CUtensorMap bmap;  // x   im2col, box 32 channels x KP pixels
     int G, xg_images, B, P, Q, Cin, Cout, KH, KW, stride, pad, bn, splits, stages;
+    int kp;            // pixels per pipeline stage: 64 when the pixel count allows (fewer, larger TMA boxes), else 32
     int T;             // filter taps accumulated per work unit (they share the dy tile): T * bn <= 256
     long Mpix, chunk;  // pixels per group; pixels per split (multiple of WG_KP)
     float* out;        // [splits][G][Cout][KH*KW][Cin]
@@ -679,7 +758,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int box_bytes = WG_KP * 128;
+    const int box_bytes = p.kp * 128;
     const int a_bytes = 4 * box_bytes;
     const int nb = p.bn / 32;                     // 32-channel boxes per tap
     const int b_bytes = (WG_NCOLS / 32) * box_bytes;
@@ -750,7 +829,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const int tap = tap0 + bt;
             const int kh = tap / p.KW, kw = tap - kh * p.KW;
             const uint32_t tx = (uint32_t)((4 + tcount * nb) * box_bytes);
-            for (long m = mbeg; m < mend; m += WG_KP) {
+            for (long m = mbeg; m < mend; m += p.kp) {
                 int img = (int)(m / (p.P * p.Q));
                 int rem = (int)(m - (long)img * p.P * p.Q);
                 int pp = rem / p.Q, qq = rem - pp * p.Q;
@@ -786,14 +865,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_NCOLS);
                 uint32_t accum = 0;
-                for (long m = mbeg; m < mend; m += WG_KP) {
+                for (long m = mbeg; m < mend; m += p.kp) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     uint32_t sb = sa + a_bytes;
                     uint64_t adesc = make_mnmajor_sw128_desc(sa, box_bytes);
-#pragma unroll
-                    for (int kk = 0; kk < WG_KP / 8; kk++) {
+                    const int nkk = p.kp / 8;
+                    for (int kk = 0; kk < nkk; kk++) {
                         // next 8 pixels = next two 512-byte K atoms: +1024 B = +64 in the 16-byte address field
                         for (int t = 0; t < tcount; t++) {
                             uint64_t bdesc = make_mnmajor_sw128_desc(sb + t * nb * box_bytes, box_bytes);
@@ -867,15 +946,17 @@ static int wg_bn(int cin) {
     return 0;
 }
 
+static int wg_kp(const cg_conv_geom& g) { return ((long)g.B * g.Ho * g.Wo) % 64 == 0 ? 64 : 32; }
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
+    const int kp = wg_kp(g);
     int bn = wg_bn(g.Cin);
     int T = WG_NCOLS / bn;
     if (T > g.KH * g.KW) T = g.KH * g.KW;
     long base = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
     init_driver();
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
-    long maxs = Mpix / (WG_KP * 16);  // at least 16 pipeline stages of work per split
+    long maxs = Mpix / (kp * 8);  // at least 8 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
     if (maxs > 64) maxs = 64;
     // pick the split count whose unit count fills whole waves best (persistent grid = #SMs), preferring >= 3 waves
@@ -889,7 +970,7 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
         if (score > best_score) { best_score = score; best = s; }
     }
     splits = best;
-    chunk = ((Mpix + splits - 1) / splits + WG_KP - 1) / WG_KP * WG_KP;
+    chunk = ((Mpix + splits - 1) / splits + kp - 1) / kp * kp;
     splits = (int)((Mpix + chunk - 1) / chunk);
 }
 
@@ -922,11 +1003,12 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         return CG_ERR_WORKSPACE;
     }
     p.bn = wg_bn(g.Cin);
+    p.kp = wg_kp(g);
     p.Mpix = (long)g.B * g.Ho * g.Wo;
     {
         cuuint64_t dims[2] = {(cuuint64_t)g.Cout, (cuuint64_t)((long)g.G * p.Mpix)};
         cuuint64_t strides[1] = {(cuuint64_t)g.Cout * 4};
-        cuuint32_t box[2] = {32, (cuuint32_t)WG_KP};
+        cuuint32_t box[2] = {32, (cuuint32_t)p.kp};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = g_encode_tiled(&p.amap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)dy, dims, strides, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -943,7 +1025,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         int lower[2] = {-g.pad, -g.pad};
         int upper[2] = {g.pad - (g.KW - 1), g.pad - (g.KH - 1)};
         cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
-        CUresult r = g_encode_im2col(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, 32, WG_KP, estr,
+        CUresult r = g_encode_im2col(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, 32, p.kp, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -958,7 +1040,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     p.out = p.splits == 1 ? dw : (float*)ws;
     p.T = WG_NCOLS / p.bn;
     if (p.T > g.KH * g.KW) p.T = g.KH * g.KW;
-    int stage_bytes = WG_KP * 128 * (4 + WG_NCOLS / 32);
+    int stage_bytes = p.kp * 128 * (4 + WG_NCOLS / 32);
     int stages = (200 * 1024) / stage_bytes;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict_
         block_reduce<1>(v, sm);
         if (threadIdx.x == 0) {
             sums[g * nseg + seg] = v[0];
-            total += __ldg(weights + seg) * (v[0] / (float)n_per_seg);
+            total += __ldg(weights + g * nseg + seg) * (v[0] / (float)n_per_seg);
         }
     }
     if (threadIdx.x == 0) loss[g] = accumulate ? loss[g] + total : total;

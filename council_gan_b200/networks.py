@@ -320,14 +320,15 @@ class CouncilGen(_StackedNet):
             w, b = w[sl:sl + 1], b[sl:sl + 1]
         return w, b
 
-    def _conv_norm(self, x, s, sl, adain, act, res, ups_out, saved):
+    def _conv_norm(self, x, s, sl, adain, act, res, ups_out, saved, ups_in=False):
         """conv(+bias) -> IN/AdaIN statistics -> normalise(+gamma/beta) -> activation (+residual).
         ups_out: the normalise pass writes its result nearest-upsampled x2 (nn.Upsample, networks.py:385), so
         the following convolution is a plain 3x3 on the materialised tensor (TMA im2col cannot halve indices)."""
         ops = self.ops
         w, b = self._w(s, sl)
         # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
-        y = ops.conv_fwd(x, w, None, s.stride, s.pad)
+        # ups_in (no-grad passes): the x2 nearest upsample is folded into this convolution (four 2x2 parity classes)
+        y = ops.conv_fwd(x, w, None, s.stride, s.pad, ups=ups_in)
         mean, rstd = ops.in_stats(y)
         off = self.adain_off.get(s.key, 0)
         z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
@@ -379,13 +380,16 @@ class CouncilGen(_StackedNet):
         adain = self._mlp(style, saved, sl)
         x = content
         nres, nup = len(self.dec_res), len(self.dec_up)
+        # passes that keep activations for backward materialise the upsampled tensor (the weight / data gradient
+        # kernels read it); no-grad passes fold the upsample into the consumer convolution instead
+        fold = saved is None
         for r, blk in enumerate(self.dec_res):
             res = x
             x = self._conv_norm(x, blk[0], sl, adain, ACT_RELU, None, False, saved)
-            x = self._conv_norm(x, blk[1], sl, adain, ACT_NONE, res, r == nres - 1 and nup > 0, saved)
+            x = self._conv_norm(x, blk[1], sl, adain, ACT_NONE, res, r == nres - 1 and nup > 0 and not fold, saved)
         for u, (a, b) in enumerate(self.dec_up):
-            x = self._conv_norm(x, a, sl, adain, ACT_RELU, None, False, saved)
-            x = self._conv_norm(x, b, sl, adain, ACT_RELU, None, u + 1 < nup, saved)
+            x = self._conv_norm(x, a, sl, adain, ACT_RELU, None, False, saved, ups_in=fold)
+            x = self._conv_norm(x, b, sl, adain, ACT_RELU, None, u + 1 < nup and not fold, saved)
         acts = [x]
         for li, s in enumerate(self.head):
             w, b = self._w(s, sl)

@@ -298,10 +298,11 @@ class CudaOps:
 
     # -- losses -----------------------------------------------------------------------------------
     def lsgan_fwd(self, out, targets, weights, nseg, loss, accumulate):
-        """out [G, nseg*B, h, w, 1]; targets/weights device [nseg]; returns sums [G,nseg] and updates
+        """out [G, nseg*B, h, w, 1]; targets device [nseg], weights device [G, nseg]; returns sums [G,nseg] and updates
         loss[G] (+)= sum_seg weights[seg] * mean_seg((out - target[seg])^2)."""
         self._chk(out, targets, weights, loss)
         G = out.shape[0]
+        assert weights.numel() == G * nseg
         n_per_seg = out[0].numel() // nseg
         sums = self.empty(G, nseg)
         self._ck(self.lib.cg_lsgan_fwd(_p(out), _p(targets), _p(weights), _p(sums), _p(loss), G, nseg, n_per_seg,

@@ -311,7 +311,7 @@ class Council_Trainer(nn.Module):
             outs = dis.forward(xin, saved)
             wdir = float(hp['gan_w']) if d == 'a2b' else 1.0  # :775 vs :777 (no gan_w on the b2a branch)
             targets = self._const('t01', [0.0, 1.0])
-            weights = self._const(('w2', wdir), [wdir, wdir])
+            weights = self._const(('w2', wdir, N), [[wdir, wdir]] * N)
             d_outs = []
             self._dis_sums[d] = []
             for out in outs:
@@ -378,7 +378,13 @@ class Council_Trainer(nn.Module):
                 pool_i.remove(j)
                 js.append(j)
             peers.append(js)
-        K = len(peers[0])
+        # a peer drawn twice (K_cfg >= N refills the pool, :865-866) gives an identical term: evaluate each distinct peer
+        # once and weight it by its multiplicity (x + x == 2x exactly)
+        uniq = [sorted(set(js)) for js in peers]
+        mult = [[js.count(j) for j in u] for js, u in zip(peers, uniq)]
+        Krun = len(peers[0])
+        U = len(uniq[0])
+        assert all(len(u) == U for u in uniq)
         total = ops.zeros(N)
         first = True
         for d in self._dirs:
@@ -395,23 +401,24 @@ class Council_Trainer(nn.Module):
                 pool = x_fake.view(N * B, H, W, IMG_C)
                 comp0 = 0
             idx = torch.tensor([[g * B + b for b in range(B)] +
-                                [comp0 + j * B + b for j in peers[g] for b in range(B)] for g in range(N)],
+                                [comp0 + j * B + b for j in uniq[g] for b in range(B)] for g in range(N)],
                                dtype=torch.int32).to(ops.device, non_blocking=True)
-            xin = ops.gather_images(pool, idx, src, N, (1 + K) * B)
+            xin = ops.gather_images(pool, idx, src, N, (1 + U) * B)
             saved = []
             outs = disc.forward(xin, saved)
             # sum_k [ mean(D(fake_i)^2) + mean((D(less_jk)-1)^2) ] * council_w / Kcfg   (:872, :878)
             wk = float(hp['council_w']) / Kcfg
-            targets = self._const(('t0k', K), [0.0] + [1.0] * K)
-            weights = self._const(('wk', K, wk), [wk * K] + [wk] * K)
+            targets = self._const(('t0k', U), [0.0] + [1.0] * U)
+            wrows = [[wk * Krun] + [wk * m for m in mult[g]] for g in range(N)]
+            weights = torch.tensor(wrows, dtype=ops.dtype).to(ops.device, non_blocking=True)
             d_outs = []
             for out in outs:
-                n_seg = out[0].numel() // (1 + K)
-                ops.lsgan_fwd(out, targets, weights, 1 + K, total, accumulate=not first)
+                n_seg = out[0].numel() // (1 + U)
+                ops.lsgan_fwd(out, targets, weights, 1 + U, total, accumulate=not first)
                 first = False
                 cf = 2.0 / (n_seg * self.world)
-                coef = self._const(('ck', K, wk, cf, N), [[wk * K * cf] + [wk * cf] * K] * N)
-                d_outs.append(ops.lsgan_bwd(out, targets, coef, 1 + K))
+                coef = torch.tensor([[v * cf for v in row] for row in wrows], dtype=ops.dtype).to(ops.device, non_blocking=True)
+                d_outs.append(ops.lsgan_bwd(out, targets, coef, 1 + U))
             disc.backward(d_outs, saved, want_wgrad=True, want_dx=False)
         total = self._global_mean(total)
         self._loss_dis_council_total = total
@@ -459,18 +466,19 @@ class Council_Trainer(nn.Module):
             cl = ops.zeros(N)
             fs = ops.zeros(N, 4)
             ones = self._const('t1', [1.0])
+            onesw = self._const(('w1', N), [[1.0]] * N)
             if gan_on:  # calc_gen_loss networks.py:84-90
                 rec['dis_saved'] = []
                 rec['dis_outs'] = self._nets['dis_' + d].forward(x_fake, rec['dis_saved'])
                 for k, out in enumerate(rec['dis_outs']):
-                    ops.lsgan_fwd(out, ones, ones, 1, adv, accumulate=k > 0)
+                    ops.lsgan_fwd(out, ones, onesw, 1, adv, accumulate=k > 0)
             if council_on:  # MsImageDisCouncil.calc_gen_loss networks.py:188-194
                 idx = self._idx(('id', N, B), lambda: [[g * B + b for b in range(B)] for g in range(N)])
                 xin = ops.gather_images(x_fake.view(N * B, H, W, IMG_C), idx, src, N, B)
                 rec['disc_saved'] = []
                 rec['disc_outs'] = self._nets['dis_council_' + d].forward(xin, rec['disc_saved'])
                 for k, out in enumerate(rec['disc_outs']):
-                    ops.lsgan_fwd(out, ones, ones, 1, cl, accumulate=k > 0)
+                    ops.lsgan_fwd(out, ones, onesw, 1, cl, accumulate=k > 0)
             if focus_on:
                 fs = ops.focus_fwd(mask, fl['mask_zero_or_one_center'], fl['mask_zero_or_one_epsilon'])
             fw[d] = rec

@@ -124,7 +124,7 @@ int cg_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int Cp, void
 
 /* ---- losses ----------------------------------------------------------------------------------- */
 /* LSGAN (networks.py:64,90,166,194).  out[G][nseg][n_per_seg]; sums[G][nseg] = sum (out-target[seg])^2;
- * loss[g] (+)= sum_seg weights[seg] * mean_seg((out-target[seg])^2).  targets/weights: device [nseg]. */
+ * loss[g] (+)= sum_seg weights[g][seg] * mean_seg((out-target[seg])^2).  targets: device [nseg]; weights: device [G][nseg]. */
 int cg_lsgan_fwd(const float* out, const float* targets, const float* weights, float* sums, float* loss,
                  int G, int nseg, int n_per_seg, int accumulate, void* stream);
 /* dout = coef[g][seg] * (out - target[seg])   (coef device pointer, [G][nseg]) */

@@ -207,7 +207,7 @@ class TorchOps:
         o = out.reshape(G, nseg, -1)
         sq = (o - targets[None, :, None]) ** 2
         sums = sq.sum(-1)
-        tot = (sq.mean(-1) * weights[None, :]).sum(-1)
+        tot = (sq.mean(-1) * weights.reshape(G, nseg)).sum(-1)
         if accumulate:
             loss += tot
         else:

@@ -201,7 +201,7 @@ def test_losses(ops, ref):
     G, nseg, B, h, w = 3, 3, 2, 5, 4
     out = rnd(G, nseg * B, h, w, 1, seed=1)
     targets = torch.tensor([0.0, 1.0, 1.0], device=DEV)
-    weights = torch.tensor([2.0, 0.5, 0.5], device=DEV)
+    weights = torch.tensor([[2.0, 0.5, 0.5], [1.0, 1.0, 0.25], [0.5, 2.0, 3.0]], device=DEV)
     loss = torch.full((G,), 3.0, device=DEV)
     rloss = loss.double().clone()
     for acc in (False, True):
