@@ -248,8 +248,14 @@ def main():
         key, (tot_ms, cnt, flops) = max(ktimes.items(), key=lambda kv: kv[1][0])
         tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2.0  # TF32 runs at half the bf16 tensor rate
         ach = flops / (tot_ms / cnt * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(key, {}).get('traffic_bytes')
+        except Exception:
+            pass
         roofline = {'bound': 'tensor', 'kernel': key, 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
-                    'traffic': None, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
+                    'frac_of_nominal_tf32_1100': ach / 1100.0, 'flops_per_launch': flops,
+                    'traffic': traffic, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
                     'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 operands)' if peaks else 'fallback 1400/2')}
     alg_tflop = 2 * ALG_GMAC_PER_IMAGE_MEMBER_256 * 1e9 * scale * n_members * batch * world / 1e12
     line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

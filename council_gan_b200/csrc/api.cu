@@ -237,3 +237,37 @@ extern "C" int cg_upsample2x_bwd(const float* d_up, float* dx, int N, int H, int
     CG_REQUIRE(C % 4 == 0, "upsample2x_bwd: C=%d must be a multiple of 4", C);
     return pool2x2_sum(d_up, dx, nullptr, nullptr, 0.f, N, H, W, C, (cudaStream_t)stream);
 }
+
+// Convolution (no bias, no activation) + instance-norm statistics of its output in one call: on the tensor path the
+// per-channel sums are produced by the convolution epilogue (no second pass over y); otherwise conv then cg_in_stats.
+extern "C" int cg_conv_fwd_stats(const cg_conv_geom* g, const float* x, const float* w, float* y, float* mean, float* rstd, float eps,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = validate_geom(*g)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = g->Ho * g->Wo;
+    int chunks = ((g_tc_mode & 1) && tc_fwd_supported(*g) && !patch_path(*g)) ? tc_fwd_stats_chunks(*g) : 0;
+    if (chunks > 0) {
+        long GBC = (long)g->G * g->B * g->Cout;
+        size_t part_bytes = ((size_t)chunks * GBC * 2 * sizeof(float) + 1023) & ~(size_t)1023;
+        size_t inner = tc_fwd_ws(*g);
+        if (part_bytes + inner > ws_bytes) {
+            set_error("conv_fwd_stats: workspace %zu < %zu bytes", ws_bytes, part_bytes + inner);
+            return CG_ERR_WORKSPACE;
+        }
+        float* part = (float*)ws;
+        if (int rc = tc_conv_fwd(*g, x, w, nullptr, y, CG_ACT_NONE, 0.f, (uint8_t*)ws + part_bytes, ws_bytes - part_bytes, st, part)) return rc;
+        return in_stats_finalize(part, mean, rstd, GBC, chunks, HW, eps, st);
+    }
+    if (int rc = cg_conv_fwd(g, x, w, nullptr, y, CG_ACT_NONE, 0.f, ws, ws_bytes, stream)) return rc;
+    return cg_in_stats(y, mean, rstd, g->G, g->B, HW, g->Cout, eps, ws, ws_bytes, stream);
+}
+extern "C" size_t cg_conv_fwd_stats_workspace_bytes(const cg_conv_geom* g) {
+    if (!g) return 0;
+    size_t a = cg_conv_workspace_bytes(g, 0);
+    long GBC = (long)g->G * g->B * g->Cout;
+    int chunks = ((g_tc_mode & 1) && tc_fwd_supported(*g) && !patch_path(*g)) ? tc_fwd_stats_chunks(*g) : 0;
+    size_t fused = chunks > 0 ? (((size_t)chunks * GBC * 2 * sizeof(float) + 1023) & ~(size_t)1023) + tc_fwd_ws(*g) : 0;
+    size_t plain = (size_t)(((long)g->Ho * g->Wo + 511) / 512) * GBC * 2 * sizeof(float);
+    size_t m = a > fused ? a : fused;
+    return m > plain ? m : plain;
+}

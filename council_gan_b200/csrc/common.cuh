@@ -73,7 +73,9 @@ int pool2x2_sum(const float* d_up, float* dx, const float* addend, const float* 
 // ---- tcgen05 TF32 implicit-GEMM convolutions (conv_tc.cu) ----
 bool tc_fwd_supported(const cg_conv_geom& g);
 int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y,
-                int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+                int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st, float* stats_part = nullptr);
+int tc_fwd_stats_chunks(const cg_conv_geom& g);
+int in_stats_finalize(const float* part, float* mean, float* rstd, long GBC, int nchunks, int HW, float eps, cudaStream_t st);
 size_t tc_fwd_ws(const cg_conv_geom& g);
 bool tc_dgrad_supported(const cg_conv_geom& g);
 size_t tc_dgrad_ws(const cg_conv_geom& g);

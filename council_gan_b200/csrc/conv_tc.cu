@@ -172,6 +172,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Column sums over the 32 rows held by the 32 lanes of a warp: a[j] of lane r is element (row r, column j); on return
+// lane j holds the sum of column j.  Transpose-reduce butterfly: at step `off` every lane keeps the half of its columns
+// selected by its lane bit and receives the partner's partial for that half -> 16+8+4+2+1 = 31 shuffles.
+__device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; i++) {
+            float send = upper ? a[i] : a[i + off];
+            float keep = upper ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
@@ -201,6 +218,8 @@ struct TcParams {
     int out_H, out_W, out_sh, out_sw;  // full output spatial size and class strides
     int w_rows_per_group;           // weight rows per group (ncls * Cout for dgrad classes)
     float* y; const float* bias; const float* addend; const float* mask_src;
+    float* stats;                   // optional [chunks][G*B*Cout][2] partial (sum, sum of squares) of the raw output, or NULL
+    long stats_gbc;                 // G*B*Cout
     int act; float slope;
     int stages;
 };
@@ -387,6 +406,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c0 = 0; c0 < p.bn; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (p.stats) {
+                    // instance-norm statistics of the raw convolution output, fused here instead of a second pass over y:
+                    // every tile lies inside one image (P*Q % 128 == 0), this warp owns 32 of its rows
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+                    const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
+                    const int tiles_per_img = pq / TC_BM;
+                    const int img = (mt * TC_BM) / pq;
+                    const int chunk = ((c * tiles_per_img + (mt - img * tiles_per_img)) << 2) + quad;
+                    const long col = (long)(g * p.B + img) * p.Cout + nt * p.bn + c0 + lane;
+                    *reinterpret_cast<float2*>(p.stats + ((long)chunk * p.stats_gbc + col) * 2) = make_float2(cs, cq);
+                }
                 if (valid) {
                     if (p.bias) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
@@ -566,10 +598,20 @@ size_t tc_fwd_ws(const cg_conv_geom& g) {
     return g.ups ? (size_t)g.G * 4 * g.Cout * 4 * g.Cin * sizeof(float) : 0;
 }
 
+// number of partial-statistics chunks the fused epilogue writes per (image, channel); 0: fusion not possible
+int tc_fwd_stats_chunks(const cg_conv_geom& g) {
+    if (pick_bn(g.Cout) < 32) return 0;
+    long pq = g.ups ? (long)g.H * g.W : (long)g.Ho * g.Wo;
+    if (pq % TC_BM != 0) return 0;
+    return (int)((g.ups ? 4 : 1) * (pq / TC_BM) * 4);
+}
+
 int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, int act, float slope, void* ws,
-                size_t ws_bytes, cudaStream_t st) {
+                size_t ws_bytes, cudaStream_t st, float* stats_part) {
     init_driver();
     TcParams p{};
+    p.stats = stats_part;
+    p.stats_gbc = (long)g.G * g.B * g.Cout;
     p.bn = pick_bn(g.Cout);
     p.n_store = p.bn == 16 ? g.Cout : p.bn;
     p.bk = pick_bk(g.Cin);

@@ -226,6 +226,11 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormP p, const floa
     }
 }
 
+int in_stats_finalize(const float* part, float* mean, float* rstd, long GBC, int nchunks, int HW, float eps, cudaStream_t st) {
+    in_stats_final_kernel<<<cdiv(GBC, 256), 256, 0, st>>>(part, mean, rstd, GBC, nchunks, HW, eps);
+    return check_launch("in_stats_final");
+}
+
 static int check_c(int C) {
     CG_REQUIRE(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "norm: unsupported channel count %d", C);
     return CG_OK;

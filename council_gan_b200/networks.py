@@ -328,8 +328,7 @@ class CouncilGen(_StackedNet):
         w, b = self._w(s, sl)
         # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
         # ups_in (no-grad passes): the x2 nearest upsample is folded into this convolution (four 2x2 parity classes)
-        y = ops.conv_fwd(x, w, None, s.stride, s.pad, ups=ups_in)
-        mean, rstd = ops.in_stats(y)
+        y, mean, rstd = ops.conv_fwd_stats(x, w, s.stride, s.pad, ups=ups_in)
         off = self.adain_off.get(s.key, 0)
         z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
         if saved is not None:

@@ -32,6 +32,8 @@ _SIGS = {
     'cg_set_tensor_core_mode': (C.c_int, [C.c_int]),
     'cg_launch_count': (C.c_uint64, []),
     'cg_conv_fwd': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_conv_fwd_stats': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_conv_fwd_stats_workspace_bytes': (C.c_size_t, [C.POINTER(ConvGeom)]),
     'cg_conv_dgrad': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_conv_wgrad': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     'cg_conv_workspace_bytes': (C.c_size_t, [C.POINTER(ConvGeom), C.c_int]),
@@ -170,6 +172,17 @@ class CudaOps:
         self._timed('conv_fwd', g, lambda: self._ck(self.lib.cg_conv_fwd(
             C.byref(g), _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ws), ws.numel(), self._stream()), 'cg_conv_fwd'))
         return y
+
+    def conv_fwd_stats(self, x, w, stride, pad, ups=False, eps=1e-5):
+        """conv (no bias / activation) + instance-norm statistics of its output: (y, mean, rstd)."""
+        self._chk(x, w)
+        g = self._geom(x.shape, w, stride, pad, ups)
+        y = self.empty(g.G, g.B, g.Ho, g.Wo, g.Cout)
+        mean, rstd = self.empty(g.G, g.B, g.Cout), self.empty(g.G, g.B, g.Cout)
+        ws = self._ws_for(self.lib.cg_conv_fwd_stats_workspace_bytes(C.byref(g)))
+        self._timed('conv_fwd', g, lambda: self._ck(self.lib.cg_conv_fwd_stats(
+            C.byref(g), _p(x), _p(w), _p(y), _p(mean), _p(rstd), eps, _p(ws), ws.numel(), self._stream()), 'cg_conv_fwd_stats'))
+        return y, mean, rstd
 
     def conv_dgrad(self, dy, w, x_shape, stride, pad, ups=False, addend=None, mask_src=None, mask_slope=0.0):
         self._chk(dy, w, addend, mask_src)

@@ -66,6 +66,12 @@ uint64_t cg_launch_count(void);
 /* y = act(conv(x, w) + bias).  bias may be NULL. */
 int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w, const float* bias, float* y,
                 int act, float slope, void* ws, size_t ws_bytes, void* stream);
+/* y = conv(x, w) (no bias, no activation) and the instance-norm statistics of y in one call (Conv2d followed by
+ * InstanceNorm2d / AdaIN, networks.py:516-518): mean, rstd [G][B][Cout].  On the tensor path the per-channel sums come
+ * out of the convolution epilogue, saving a pass over y. */
+int cg_conv_fwd_stats(const cg_conv_geom* g, const float* x, const float* w, float* y, float* mean, float* rstd,
+                      float eps, void* ws, size_t ws_bytes, void* stream);
+size_t cg_conv_fwd_stats_workspace_bytes(const cg_conv_geom* g);
 /* dx = (conv_transpose(dy, w) [+ addend]) * act'(mask_src)      (autograd of the call above)
  * dx has the STORED input shape; with g->ups the 2x2 upsample fan-in is summed.
  * addend / mask_src (same shape as dx) may be NULL; act' = mask_src > 0 ? 1 : mask_slope. */

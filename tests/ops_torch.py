@@ -63,6 +63,11 @@ class TorchOps:
     def conv_fwd(self, x, w, bias, stride, pad, ups=False, act=ACT_NONE, slope=0.2):
         return _act(self._conv_pre(x, w, bias, stride, pad, ups), act, slope)
 
+    def conv_fwd_stats(self, x, w, stride, pad, ups=False, eps=1e-5):
+        y = self.conv_fwd(x, w, None, stride, pad, ups=ups)
+        mean, rstd = self.in_stats(y, eps)
+        return y, mean, rstd
+
     def conv_dgrad(self, dy, w, x_shape, stride, pad, ups=False, addend=None, mask_src=None, mask_slope=0.0):
         G = w.shape[0]
         x = torch.zeros((G,) + tuple(x_shape[1:]), dtype=dy.dtype, device=dy.device, requires_grad=True)

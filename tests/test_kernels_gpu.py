@@ -109,6 +109,39 @@ def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
         ops.set_tensor_core_mode(1)
 
 
+STATS_CASES = [
+    # name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups
+    ('stats_res_3x3_256', 2, 2, 2, 16, 16, 256, 256, 3, 1, 1, False),
+    ('stats_down_4x4s2', 2, 2, 2, 32, 32, 64, 128, 4, 2, 1, False),
+    ('stats_up_classes', 2, 2, 2, 16, 16, 128, 64, 3, 1, 1, True),
+    ('stats_first_7x7_patch', 2, 1, 2, 16, 16, 4, 64, 7, 1, 3, False),
+    ('stats_small_map_simt', 2, 2, 1, 8, 8, 256, 256, 3, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', STATS_CASES, ids=[c[0] for c in STATS_CASES])
+@pytest.mark.parametrize('tc', [0, 1])
+def test_conv_fwd_stats(ops, ref, case, tc):
+    """conv + fused instance-norm statistics (tensor-core epilogue) vs conv followed by a separate statistics pass."""
+    name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups = case
+    ops.set_tensor_core_mode(tc)
+    try:
+        x = rnd(Gx, B, H, W, Cin, seed=11) + 0.3
+        w = rnd(G, Cout, K, K, Cin, seed=12, scale=0.1)
+        y, mean, rstd = ops.conv_fwd_stats(x, w, stride, pad, ups=ups)
+        ry, rm, rr = ref.conv_fwd_stats(d(x), d(w), stride, pad, ups=ups)
+        tol = 2e-5 if tc == 0 else 4e-3
+        check(y, ry, tol, name + ' y')
+        # statistics must describe the y that was actually produced (TF32 or fp32), to fp32 accuracy
+        m2 = y.double().mean(dim=(2, 3))
+        v2 = y.double().var(dim=(2, 3), unbiased=False)
+        check(mean, m2, 2e-5, name + ' mean of own output')
+        check(rstd, 1.0 / torch.sqrt(v2 + 1e-5), 5e-5, name + ' rstd of own output')
+        check(mean, rm, tol * 4, name + ' mean vs fp64 reference')
+    finally:
+        ops.set_tensor_core_mode(1)
+
+
 def test_conv_wgrad_split_k_large(ops, ref):
     """Many pixels, few output tiles -> split-K with the deterministic two-phase reduction."""
     x = rnd(1, 2, 64, 64, 8, seed=1)
