@@ -18,6 +18,7 @@ Per-member ``state_dict`` views keep the reference's key names and OIHW shapes (
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -218,6 +219,8 @@ class CouncilGen(_StackedNet):
         assert g['pad_type'] == 'zero' and g['activ'] == 'relu'
         assert input_dim == 3 and g['num_of_mask_dim_to_add'] == 3, 'mask head kernel is specialised for RGB + 3 masks'
         self.ops, self.hp, self.G = ops, hp, G
+        # statistics in the convolution epilogue (cg_conv_fwd_stats) vs a separate pass; see profiles/r01_summary.md
+        self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', '0') == '1'  # measured: +5.2 ms of epilogue vs -2.6 ms saved -> off by default
         self.dim, self.style_dim, self.nd, self.nr, self.mlp_dim = g['dim'], g['style_dim'], g['n_downsample'], g['n_res'], g['mlp_dim']
         dim, nd, nr = self.dim, self.nd, self.nr
         img_lanes = [0, 1, 2]
@@ -328,7 +331,11 @@ class CouncilGen(_StackedNet):
         w, b = self._w(s, sl)
         # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
         # ups_in (no-grad passes): the x2 nearest upsample is folded into this convolution (four 2x2 parity classes)
-        y, mean, rstd = ops.conv_fwd_stats(x, w, s.stride, s.pad, ups=ups_in)
+        if self.fuse_stats:
+            y, mean, rstd = ops.conv_fwd_stats(x, w, s.stride, s.pad, ups=ups_in)
+        else:
+            y = ops.conv_fwd(x, w, None, s.stride, s.pad, ups=ups_in)
+            mean, rstd = ops.in_stats(y)
         off = self.adain_off.get(s.key, 0)
         z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
         if saved is not None:
