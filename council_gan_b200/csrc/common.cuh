@@ -12,6 +12,8 @@ namespace cg {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 extern int g_tc_mode;
+extern int g_pair_mode;
+extern int g_pair_cap;
 
 inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -17,6 +17,8 @@ CASES = [
     ('4x4s2_c256_o512', 'fwd', 2, 2, 2, 32, 32, 256, 512, 4, 2, 1),
     ('3x3_partial_tile', 'fwd', 2, 2, 3, 12, 12, 64, 64, 3, 1, 1),
     ('3x3_many_tiles', 'fwd', 4, 4, 4, 64, 64, 256, 256, 3, 1, 1),
+    ('pair_half_tile', 'fwd', 2, 2, 5, 8, 16, 64, 256, 3, 1, 1),
+    ('pair_partial', 'fwd', 2, 2, 3, 12, 20, 32, 512, 3, 1, 1),
     ('dgrad_3x3', 'dgrad', 2, 2, 2, 16, 16, 128, 256, 3, 1, 1),
     ('dgrad_1x1', 'dgrad', 2, 2, 2, 16, 16, 64, 64, 1, 1, 0),
     ('dgrad_4x4s2', 'dgrad', 2, 2, 2, 32, 32, 64, 128, 4, 2, 1),
@@ -91,7 +93,7 @@ if __name__ == '__main__':
     else:
         only = os.environ.get('TC_ONLY', '')
         for i, c in enumerate(CASES):
-            if only and only not in c[1]:
+            if only and c[1] not in only.split(','):
                 continue
             try:
                 r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=45)

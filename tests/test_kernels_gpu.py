@@ -63,6 +63,11 @@ CONV_CASES = [
     ('tc_dc_1x1_512_512', 3, 3, 4, 8, 8, 512, 512, 1, 1, 0, False),
     ('tc_shared_input', 3, 1, 2, 16, 16, 64, 64, 3, 1, 1, False),
     ('tc_partial_tiles', 2, 2, 3, 12, 20, 64, 128, 3, 1, 1, False),
+    # CTA-pair kernel (Cout % 256 == 0, >= 512 pixels): 640 px = 2.5 pair tiles (second CTA of the last pair idle),
+    # 720 px (partial second CTA), dgrad classes of a stride-2 layer
+    ('tc_pair_half_tile', 2, 2, 5, 8, 16, 64, 256, 3, 1, 1, False),
+    ('tc_pair_partial', 2, 2, 3, 12, 20, 32, 512, 3, 1, 1, False),
+    ('tc_pair_dgrad_s2', 2, 2, 2, 32, 32, 256, 64, 4, 2, 1, False),
     # image-side layers on the explicit-patch path (im2col -> 1x1 tensor-core GEMM)
     ('patch_disc0_3x3_pair', 2, 2, 2, 16, 16, 8, 64, 3, 1, 1, False),
     ('patch_dis0_4x4s2_img', 2, 2, 4, 16, 16, 4, 64, 4, 2, 1, False),
