@@ -41,7 +41,7 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static int g_sm_count = 0;
 int g_pair_cap = 0;
-int g_pair_mode = 1;  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
+int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
 static int g_driver_version = 0;
 static std::once_flag g_once;
 
@@ -551,8 +551,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on `
                  : "memory");
 }
 
-constexpr int TC2_BN = 256;
-constexpr int TC2_STAGES = 6;  // 6 x (16 KB A + 16 KB half-B)
+constexpr int TC2_MAX_STAGES = 12;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -560,18 +559,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     constexpr int BK = TC_BK;
-    constexpr int a_bytes = TC_BM * BK * 4;      // 16 KB: this CTA's 128 pixel rows
-    constexpr int b_bytes = 128 * BK * 4;        // 16 KB: this CTA's half of the 256 weight rows
-    constexpr int stage_bytes = a_bytes + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)TC2_STAGES * stage_bytes);
-    uint64_t* empty_bar = full_bar + TC2_STAGES;
-    uint64_t* tfull_bar = empty_bar + TC2_STAGES;
+    constexpr int a_bytes = TC_BM * BK * 4;      // 16 KB: one K chunk of this CTA's 128 pixel rows
+    const int b_bytes = (p.bn / 2) * BK * 4;     // 4 / 8 / 16 KB: one K chunk of this CTA's half of the bn weight rows
+    const int stage_bytes = p.cps * (a_bytes + b_bytes);  // [A_0..A_cps-1][B_0..B_cps-1]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int pq = p.P * p.Q;
     const int PT = (p.B * pq + 2 * TC_BM - 1) / (2 * TC_BM);  // pair tiles (256 pixels) per (group, class)
-    const int NT = p.Cout / TC2_BN;
+    const int NT = p.Cout / p.bn;
     const int tiles = p.G * p.ncls * NT * PT;
     const int kchunks = p.Cin / BK;
     const int kiters = p.KH * p.KW * kchunks;
@@ -583,7 +582,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     }
     if (warp == TC_MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < TC2_STAGES; s++) {
+            for (int s = 0; s < p.stages; s++) {
                 mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx covers the bytes of BOTH CTAs (the peer only issues TMA)
                 mbar_init(&empty_bar[s], 1);  // multicast commit
             }
@@ -622,27 +621,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 int n_coord = g * p.xg_images + img;
                 int w_coord = cl.w0 + qq * p.stride;
                 int h_coord = cl.h0 + pp * p.stride;
-                int wrow = g * p.w_rows_per_group + cl.wrow_off + nt * TC2_BN + (int)rank * 128;
+                int wrow = g * p.w_rows_per_group + cl.wrow_off + nt * p.bn + (int)rank * (p.bn >> 1);
                 int kh = 0, kw = 0, kc = 0;
-                for (int k = 0; k < kiters; k++) {
+                for (int k0 = 0; k0 < kiters; k0 += p.cps) {
+                    const int n = kiters - k0 < p.cps ? kiters - k0 : p.cps;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
+                    uint8_t* sb = sa + p.cps * a_bytes;
                     const uint32_t full_leader = leader_addr(smem_u32(&full_bar[stage]));
                     // both CTAs' A + half-B land on the leader's barrier; a peer box that lands before this expect_tx only drives
                     // the transaction count negative for a moment (the phase cannot complete before the leader's arrival)
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
-                    tma2_load_im2col_4d(&cl.amap, full_leader, sa, kc * BK, w_coord, h_coord, n_coord, (uint16_t)kw, (uint16_t)kh);
-                    tma2_load_2d(&p.bmap, full_leader, sb, (kh * p.KW + kw) * p.Cin + kc * BK, wrow);
-                    if (++kc == kchunks) { kc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
-                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * n * (a_bytes + b_bytes)));
+                    for (int j = 0; j < n; j++) {
+                        tma2_load_im2col_4d(&cl.amap, full_leader, sa + j * a_bytes, kc * BK, w_coord, h_coord, n_coord, (uint16_t)kw,
+                                            (uint16_t)kh);
+                        tma2_load_2d(&p.bmap, full_leader, sb + j * b_bytes, (kh * p.KW + kw) * p.Cin + kc * BK, wrow);
+                        if (++kc == kchunks) { kc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == TC_MMA_WARP) {
         if (lane == 0 && rank == 0) {
-            // kind::tf32, D=F32, K-major A and B, M = 256 (both CTAs), N = 256
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            // kind::tf32, D=F32, K-major A and B, M = 256 (both CTAs), N = bn
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint64_t desc_hi = make_kmajor_sw128_desc(0);
             int stage = 0;
             uint32_t phase = 0;
@@ -651,18 +654,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             for (int t = cluster_id; t < tiles; t += nclusters) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC2_BN);
-                for (int k = 0; k < kiters; k++) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+                for (int k0 = 0; k0 < kiters; k0 += p.cps) {
+                    const int n = kiters - k0 < p.cps ? kiters - k0 : p.cps;
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = desc_hi | (uint64_t)((sa & 0x3FFFF) >> 4);
-                    const uint64_t bdesc = desc_hi | (uint64_t)(((sa + a_bytes) & 0x3FFFF) >> 4);
+                    const uint32_t sb = sa + p.cps * a_bytes;
+                    for (int j = 0; j < n; j++) {
+                        const uint64_t adesc = desc_hi | (uint64_t)(((sa + j * a_bytes) & 0x3FFFF) >> 4);
+                        const uint64_t bdesc = desc_hi | (uint64_t)(((sb + j * b_bytes) & 0x3FFFF) >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; kk++)
-                        umma2_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < BK / 8; kk++)
+                            umma2_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k0 | j | kk) != 0 ? 1u : 0u);
+                    }
                     umma2_commit_mc(&empty_bar[stage]);
-                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma2_commit_mc(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -691,15 +698,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 int rem = m - img * pq;
                 int pp = rem / p.Q, qq = rem - pp * p.Q;
                 long pix = ((long)(g * p.B + img) * p.out_H + (pp * p.out_sh + cl.out_h0)) * p.out_W + (qq * p.out_sw + cl.out_w0);
-                out_off = pix * p.Cout + nt * TC2_BN;
+                out_off = pix * p.Cout + nt * p.bn;
             }
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC2_BN);
-            for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 if (valid) {
                     if (p.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * TC2_BN + c0);
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             float4 a = __ldg(bp + j);
@@ -851,9 +858,10 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     }
     int MT = cdiv((long)p.B * p.P * p.Q, TC_BM);
     long tiles = (long)p.G * p.ncls * ((p.Cout + p.bn - 1) / p.bn) * MT;
-    // CTA pairs for the 256-wide layers (halves the per-SM weight-operand traffic); needs an even SM count and enough pair tiles
-    if (g_pair_mode && p.bn == 256 && p.bk == 32 && p.Cout % 256 == 0 && p.Cin % 32 == 0 && !p.stats && p.act != CG_ACT_TANH &&
-        (long)p.B * p.P * p.Q >= 512) {
+    // CTA pairs (cta_group::2): one MMA spans two SMs, each staging its own 128 pixel rows and HALF of the weight rows -> less
+    // shared-memory operand traffic per SM (wide layers) and half the MMA instructions per pixel (narrow layers, issue-bound)
+    if (((p.bn == 256 && (g_pair_mode & 1)) || (p.bn == 128 && (g_pair_mode & 2)) || (p.bn == 64 && (g_pair_mode & 4))) && p.bk == 32 && p.Cout % p.bn == 0 && p.Cin % 32 == 0 && !p.stats &&
+        p.act != CG_ACT_TANH && (long)p.B * p.P * p.Q >= 512) {
         static bool attr2_set = false;
         if (!attr2_set) {
             cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -863,15 +871,17 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
             }
             attr2_set = true;
         }
-        if (int rc = encode_weights_map(&p.bmap, p.w_base, p.w_rows, p.w_ktot, 128, 32)) return rc;  // each CTA stages half of the 256 rows
-        long ptiles = (long)p.G * p.ncls * (p.Cout / 256) * cdiv((long)p.B * p.P * p.Q, 2 * TC_BM);
-        size_t smem2 = (size_t)TC2_STAGES * (TC_BM * TC_BK * 4 + 128 * TC_BK * 4) + 1024 + (2 * TC2_STAGES + 4) * 8 + 32;
+        const int stage2 = p.cps * (TC_BM * TC_BK * 4 + (p.bn / 2) * TC_BK * 4);
+        int stages2 = (226 * 1024 - 1536) / stage2;
+        if (stages2 > TC2_MAX_STAGES) stages2 = TC2_MAX_STAGES;
+        p.stages = stages2;
+        size_t smem2 = (size_t)stages2 * stage2 + 1024 + (2 * TC2_MAX_STAGES + 4) * 8 + 32;
         static int max_pairs = 0;  // co-resident CTA pairs (GPCs with an odd SM count strand one SM each)
         if (!max_pairs) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2 * (g_sm_count / 2));
             cfg.blockDim = dim3(TC_THREADS);
-            cfg.dynamicSmemBytes = smem2;
+            cfg.dynamicSmemBytes = 220 * 1024;
             cudaLaunchAttribute at;
             at.id = cudaLaunchAttributeClusterDimension;
             at.val.clusterDim.x = 2;
@@ -888,7 +898,8 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
             max_pairs = n < g_sm_count / 2 ? n : g_sm_count / 2;
         }
         int pairs = g_pair_cap > 0 && g_pair_cap < max_pairs ? g_pair_cap : max_pairs;
-        if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "conv_tc2: max_pairs=%d pairs=%d ptiles=%ld\n", max_pairs, pairs, (long)p.G * p.ncls * (p.Cout / 256) * cdiv((long)p.B * p.P * p.Q, 2 * TC_BM));
+        if (int rc = encode_weights_map(&p.bmap, p.w_base, p.w_rows, p.w_ktot, p.bn / 2, 32)) return rc;  // each CTA stages half of the rows
+        long ptiles = (long)p.G * p.ncls * (p.Cout / p.bn) * cdiv((long)p.B * p.P * p.Q, 2 * TC_BM);
         int nclusters = (int)(ptiles < pairs ? ptiles : pairs);
         conv_tc2_kernel<<<2 * nclusters, TC_THREADS, smem2, st>>>(p);
         return check_launch("conv_tc2_kernel");
