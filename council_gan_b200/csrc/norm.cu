@@ -9,7 +9,8 @@
 
 namespace cg {
 
-constexpr int ST_ROWS = 512;  // pixels per partial-reduction block
+constexpr int ST_ROWS = 128;  // pixels per block (and per partial sum): 1024+ blocks on the 64x64x256 maps, one resident wave
+constexpr int ST_U = 4;       // rows in flight per thread: independent 16-byte loads issued before their first use
 
 // lanes = C/4 threads span the channel axis, 256/lanes threads stride the pixel axis.
 struct LaneMap {
@@ -35,10 +36,18 @@ __global__ void __launch_bounds__(256) in_stats_partial_kernel(const float* __re
     const float* base = y + ((long)gb * HW) * C + lm.lane * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     if (lm.rl < lm.rowl)
-        for (int r = r0 + lm.rl; r < r1; r += lm.rowl) {
-            float4 v = f4ld(base + (long)r * C);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+        for (int r = r0 + lm.rl; r < r1; r += ST_U * lm.rowl) {
+            float4 v[ST_U];
+#pragma unroll
+            for (int u = 0; u < ST_U; u++) {
+                const int rr = r + u * lm.rowl;
+                v[u] = rr < r1 ? f4ld(base + (long)rr * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < ST_U; u++) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q.x += v[u].x * v[u].x; q.y += v[u].y * v[u].y; q.z += v[u].z * v[u].z; q.w += v[u].w * v[u].w;
+            }
         }
     sm[0][threadIdx.x] = s;
     sm[1][threadIdx.x] = q;
@@ -99,26 +108,39 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormP p) {
     const int r0 = blockIdx.x * ST_ROWS, r1 = min(HW, r0 + ST_ROWS);
     const float* yb = p.y + (long)gb * HW * p.C + c;
     const float* rb = p.res ? p.res + (long)gb * HW * p.C + c : nullptr;
-    for (int r = r0 + lm.rl; r < r1; r += lm.rowl) {
-        float4 v = f4ld(yb + (long)r * p.C);
-        v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
-        if (p.act == CG_ACT_RELU) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    for (int r = r0 + lm.rl; r < r1; r += ST_U * lm.rowl) {
+        float4 v[ST_U], e[ST_U];
+#pragma unroll
+        for (int u = 0; u < ST_U; u++) {
+            const int rr = r + u * lm.rowl;
+            if (rr < r1) {
+                v[u] = f4ld(yb + (long)rr * p.C);
+                if (rb) e[u] = f4ld(rb + (long)rr * p.C);
+            }
         }
-        if (rb) {
-            float4 e = f4ld(rb + (long)r * p.C);
-            v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-        }
-        if (!p.ups) {
-            *reinterpret_cast<float4*>(p.z + ((long)gb * HW + r) * p.C + c) = v;
-        } else {
-            int h = r / p.W, w = r - h * p.W;
-            long W2 = 2L * p.W;
-            float* zp = p.z + (((long)gb * 2 * p.H + 2 * h) * W2 + 2 * w) * p.C + c;
-            *reinterpret_cast<float4*>(zp) = v;
-            *reinterpret_cast<float4*>(zp + p.C) = v;
-            *reinterpret_cast<float4*>(zp + W2 * p.C) = v;
-            *reinterpret_cast<float4*>(zp + W2 * p.C + p.C) = v;
+#pragma unroll
+        for (int u = 0; u < ST_U; u++) {
+            const int rr = r + u * lm.rowl;
+            if (rr >= r1) break;
+            float4 o;
+            o.x = fmaf(v[u].x, a.x, b.x); o.y = fmaf(v[u].y, a.y, b.y); o.z = fmaf(v[u].z, a.z, b.z); o.w = fmaf(v[u].w, a.w, b.w);
+            if (p.act == CG_ACT_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (rb) {
+                o.x += e[u].x; o.y += e[u].y; o.z += e[u].z; o.w += e[u].w;
+            }
+            if (!p.ups) {
+                *reinterpret_cast<float4*>(p.z + ((long)gb * HW + rr) * p.C + c) = o;
+            } else {
+                int h = rr / p.W, w = rr - h * p.W;
+                long W2 = 2L * p.W;
+                float* zp = p.z + (((long)gb * 2 * p.H + 2 * h) * W2 + 2 * w) * p.C + c;
+                *reinterpret_cast<float4*>(zp) = o;
+                *reinterpret_cast<float4*>(zp + p.C) = o;
+                *reinterpret_cast<float4*>(zp + W2 * p.C) = o;
+                *reinterpret_cast<float4*>(zp + W2 * p.C + p.C) = o;
+            }
         }
     }
 }
@@ -147,18 +169,32 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(NormP p) {
     const float* yb = p.y + (long)gb * HW * p.C + c;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     if (lm.rl < lm.rowl)
-        for (int r = r0 + lm.rl; r < r1; r += lm.rowl) {
-            float4 v = f4ld(yb + (long)r * p.C);
-            float4 g1 = load_dz(p, gb, r, c);
-            if (p.act == CG_ACT_RELU) {
-                if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
-                if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
-                if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
-                if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+        for (int r = r0 + lm.rl; r < r1; r += ST_U * lm.rowl) {
+            float4 vv[ST_U], gg[ST_U];
+#pragma unroll
+            for (int u = 0; u < ST_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr < r1) {
+                    vv[u] = f4ld(yb + (long)rr * p.C);
+                    gg[u] = load_dz(p, gb, rr, c);
+                } else {
+                    vv[u] = mu;
+                    gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-            s.x += g1.x; s.y += g1.y; s.z += g1.z; s.w += g1.w;
-            q.x += g1.x * (v.x - mu.x) * rs.x; q.y += g1.y * (v.y - mu.y) * rs.y;
-            q.z += g1.z * (v.z - mu.z) * rs.z; q.w += g1.w * (v.w - mu.w) * rs.w;
+#pragma unroll
+            for (int u = 0; u < ST_U; u++) {
+                float4 v = vv[u], g1 = gg[u];
+                if (p.act == CG_ACT_RELU) {
+                    if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
+                    if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
+                    if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
+                    if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+                }
+                s.x += g1.x; s.y += g1.y; s.z += g1.z; s.w += g1.w;
+                q.x += g1.x * (v.x - mu.x) * rs.x; q.y += g1.y * (v.y - mu.y) * rs.y;
+                q.z += g1.z * (v.z - mu.z) * rs.z; q.w += g1.w * (v.w - mu.w) * rs.w;
+            }
         }
     sm[0][threadIdx.x] = s;
     sm[1][threadIdx.x] = q;
@@ -208,21 +244,34 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormP p, const floa
     float m2[4] = {sp[1] * inv, sp[3] * inv, sp[5] * inv, sp[7] * inv};
     const int r0 = blockIdx.x * ST_ROWS, r1 = min(HW, r0 + ST_ROWS);
     const float* yb = p.y + (long)gb * HW * p.C + c;
-    for (int r = r0 + lm.rl; r < r1; r += lm.rowl) {
-        float4 v = f4ld(yb + (long)r * p.C);
-        float4 g1 = load_dz(p, gb, r, c);
-        if (p.act == CG_ACT_RELU) {
-            if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
-            if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
-            if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
-            if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+    for (int r = r0 + lm.rl; r < r1; r += ST_U * lm.rowl) {
+        float4 vv[ST_U], gg[ST_U];
+#pragma unroll
+        for (int u = 0; u < ST_U; u++) {
+            const int rr = r + u * lm.rowl;
+            if (rr < r1) {
+                vv[u] = f4ld(yb + (long)rr * p.C);
+                gg[u] = load_dz(p, gb, rr, c);
+            }
         }
-        float4 o;
-        o.x = a.x * (g1.x - m1[0] - (v.x - mu.x) * rs.x * m2[0]);
-        o.y = a.y * (g1.y - m1[1] - (v.y - mu.y) * rs.y * m2[1]);
-        o.z = a.z * (g1.z - m1[2] - (v.z - mu.z) * rs.z * m2[2]);
-        o.w = a.w * (g1.w - m1[3] - (v.w - mu.w) * rs.w * m2[3]);
-        *reinterpret_cast<float4*>(p.dy + ((long)gb * HW + r) * p.C + c) = o;
+#pragma unroll
+        for (int u = 0; u < ST_U; u++) {
+            const int rr = r + u * lm.rowl;
+            if (rr >= r1) break;
+            float4 v = vv[u], g1 = gg[u];
+            if (p.act == CG_ACT_RELU) {
+                if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
+                if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
+                if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
+                if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+            }
+            float4 o;
+            o.x = a.x * (g1.x - m1[0] - (v.x - mu.x) * rs.x * m2[0]);
+            o.y = a.y * (g1.y - m1[1] - (v.y - mu.y) * rs.y * m2[1]);
+            o.z = a.z * (g1.z - m1[2] - (v.z - mu.z) * rs.z * m2[2]);
+            o.w = a.w * (g1.w - m1[3] - (v.w - mu.w) * rs.w * m2[3]);
+            *reinterpret_cast<float4*>(p.dy + ((long)gb * HW + rr) * p.C + c) = o;
+        }
     }
 }
 

@@ -210,7 +210,7 @@ class CudaOps:
         self._chk(y)
         G, B, H, W, Cc = y.shape
         mean, rstd = self.empty(G, B, Cc), self.empty(G, B, Cc)
-        ws = self._ws_for(((H * W + 511) // 512) * G * B * Cc * 8)
+        ws = self._ws_for(((H * W + 127) // 128) * G * B * Cc * 8)
         self._ck(self.lib.cg_in_stats(_p(y), _p(mean), _p(rstd), G, B, H * W, Cc, eps, _p(ws), ws.numel(),
                                       self._stream()), 'cg_in_stats')
         return mean, rstd
@@ -229,7 +229,7 @@ class CudaOps:
         G, B, H, W, Cc = y.shape
         dy = self.empty(G, B, H, W, Cc)
         P = adain.shape[-1] if adain is not None else 0
-        ws = self._ws_for((((H * W + 511) // 512) + 1) * G * B * Cc * 8)
+        ws = self._ws_for((((H * W + 127) // 128) + 1) * G * B * Cc * 8)
         self._ck(self.lib.cg_norm_act_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
                                           G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
                  'cg_norm_act_bwd')
