@@ -476,9 +476,14 @@ int simt_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, floa
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradient): db[g][c] = sum_rows dy[g][row][c]
 // ------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS = 1024;
+// rows per partial sum: >= 128 and at most 256 partials per group, so the 64x64x256 maps launch 1024 blocks instead of 128
+static inline int cs_rows(long rows) {
+    long r = (rows + 255) / 256;
+    r = (r + 63) / 64 * 64;
+    return (int)(r < 128 ? 128 : r);
+}
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
-                                                             long rows, int C, int nchunks) {
+                                                             long rows, int C, int nchunks, int CS_ROWS) {
     __shared__ float sm[256];
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C < 256 ? C : 256;
@@ -510,7 +515,8 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
     out[i] = s;
 }
 // float4-vectorised variant for C % 4 == 0, C/4 dividing 256: lanes = C/4 threads across channels, 256/lanes row lanes
-__global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __restrict__ dy, float* __restrict__ part, long rows, int C) {
+__global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __restrict__ dy, float* __restrict__ part, long rows, int C,
+                                                                int CS_ROWS) {
     __shared__ float4 sm[256];
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int lanes = C >> 2, rowl = 256 / lanes;
@@ -518,16 +524,15 @@ __global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __r
     const long r0 = (long)chunk * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
     const float* base = dy + (long)g * rows * C + lane * 4;
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-    long r = r0 + rl;
-    for (; r + rowl < r1; r += 2 * rowl) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(base + r * C));
-        float4 b = __ldg(reinterpret_cast<const float4*>(base + (r + rowl) * C));
-        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
-        s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
-    }
-    if (r < r1) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(base + r * C));
-        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+    for (long r = r0 + rl; r < r1; r += 4 * rowl) {  // four independent 16-byte loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long rr = r + (long)u * rowl;
+            v[u] = rr < r1 ? __ldg(reinterpret_cast<const float4*>(base + rr * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        s0.x += v[0].x + v[2].x; s0.y += v[0].y + v[2].y; s0.z += v[0].z + v[2].z; s0.w += v[0].w + v[2].w;
+        s1.x += v[1].x + v[3].x; s1.y += v[1].y + v[3].y; s1.z += v[1].z + v[3].z; s1.w += v[1].w + v[3].w;
     }
     s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
     sm[threadIdx.x] = s0;
@@ -540,18 +545,19 @@ __global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __r
         *reinterpret_cast<float4*>(part + ((long)chunk * gridDim.y + g) * C + lane * 4) = s0;
     }
 }
-size_t colsum_ws(int G, long rows, int C) { return (size_t)cdiv(rows, CS_ROWS) * G * C * sizeof(float); }
+size_t colsum_ws(int G, long rows, int C) { return (size_t)cdiv(rows, cs_rows(rows)) * G * C * sizeof(float); }
 int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
     size_t need = colsum_ws(G, rows, C);
     if (need > ws_bytes) {
         set_error("colsum: workspace %zu < %zu bytes", ws_bytes, need);
         return CG_ERR_WORKSPACE;
     }
-    int nchunks = cdiv(rows, CS_ROWS);
+    const int csr = cs_rows(rows);
+    int nchunks = cdiv(rows, csr);
     if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
-        colsum_partial_v4_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C);
+        colsum_partial_v4_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, csr);
     else
-        colsum_partial_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, nchunks);
+        colsum_partial_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, nchunks, csr);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
     colsum_final_kernel<<<cdiv((long)G * C, 256), 256, 0, st>>>((const float*)ws, db, G * C, nchunks);

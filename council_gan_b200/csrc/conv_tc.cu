@@ -41,7 +41,8 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static int g_sm_count = 0;
 int g_pair_cap = 0;
-int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
+int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
+                      // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
 static int g_driver_version = 0;
 static std::once_flag g_once;
 
@@ -1312,6 +1313,184 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     }
 }
 
+// CTA-pair variant of the weight gradient: one 256-cout x N tile per pair.  Each CTA stages dy for its own 128 output
+// channels and HALF of the x columns of every tap (N/2), so a 64-pixel stage is 64 KB instead of 96 KB (3 stages deep
+// instead of 2, 8 TMA boxes instead of 12) and the x tile crosses L2 -> shared memory once per 256 output channels.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad_tc2_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int box_bytes = p.kp * 128;
+    const int a_bytes = 4 * box_bytes;
+    const int nb2 = p.bn / 64;                    // 32-channel boxes per tap staged by THIS CTA (half of the tap's N)
+    const int b_bytes = (WG_NCOLS / 64) * box_bytes;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int taps = p.KH * p.KW;
+    const int TG = (taps + p.T - 1) / p.T;
+    const int COT = p.Cout / 256;
+    const int CIT = p.Cin / p.bn;
+    const int units = p.G * COT * p.splits * CIT * TG;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (warp == TC_PRODUCER_WARP && lane == 0) {
+        prefetch_tmap(&p.amap);
+        prefetch_tmap(&p.bmap);
+    }
+    if (warp == TC_MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; s++) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int a = 0; a < 2; a++) {
+                mbar_init(&tfull_bar[a], 1);
+                mbar_init(&tempty_bar[a], 256);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * WG_NCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int u, int& g, int& cot, int& sp, int& cit, int& tg) {
+        tg = u % TG; u /= TG;
+        cit = u % CIT; u /= CIT;
+        sp = u % p.splits; u /= p.splits;
+        cot = u % COT;
+        g = u / COT;
+    };
+
+    if (warp == TC_PRODUCER_WARP) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = cluster_id; u < units; u += nclusters) {
+            int g, cot, sp, cit, tg;
+            decode(u, g, cot, sp, cit, tg);
+            const int tap0 = tg * p.T;
+            const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
+            const long mbeg = (long)sp * p.chunk;
+            const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
+            // lane roles: 0..3 -> dy boxes of this CTA's 128 couts; 4..4+tcount*nb2 -> this CTA's half of each tap's x boxes
+            const int q = lane - 4;
+            const bool is_a = lane < 4;
+            const bool is_b = q >= 0 && q < tcount * nb2;
+            const int bt = is_b ? q / nb2 : 0, bj = is_b ? q - bt * nb2 : 0;
+            const int tap = tap0 + bt;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const uint32_t tx = (uint32_t)(2 * (4 + tcount * nb2) * box_bytes);  // both CTAs' boxes land on the leader's barrier
+            for (long m = mbeg; m < mend; m += p.kp) {
+                int img = (int)(m / (p.P * p.Q));
+                int rem = (int)(m - (long)img * p.P * p.Q);
+                int pp = rem / p.Q, qq = rem - pp * p.Q;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                const uint32_t full_leader = leader_addr(smem_u32(&full_bar[stage]));
+                if (lane == 0 && rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                __syncwarp();
+                if (is_a)
+                    tma2_load_2d(&p.amap, full_leader, sa + lane * box_bytes, cot * 256 + (int)rank * 128 + lane * 32,
+                                 (int)((long)g * p.Mpix + m));
+                if (is_b)
+                    tma2_load_im2col_4d(&p.bmap, full_leader, sb + q * box_bytes, cit * p.bn + (int)rank * (p.bn >> 1) + bj * 32,
+                                        -p.pad + qq * p.stride, -p.pad + pp * p.stride, g * p.xg_images + img, (uint16_t)kw, (uint16_t)kh);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        if (lane == 0 && rank == 0) {
+            // kind::tf32, D=F32, A and B MN-major (bits 15, 16), M = 256 (both CTAs), N = bn
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = cluster_id; u < units; u += nclusters) {
+                int g, cot, sp, cit, tg;
+                decode(u, g, cot, sp, cit, tg);
+                const int tap0 = tg * p.T;
+                const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
+                const long mbeg = (long)sp * p.chunk;
+                const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_NCOLS);
+                uint32_t accum = 0;
+                for (long m = mbeg; m < mend; m += p.kp) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    uint32_t sb = sa + a_bytes;
+                    uint64_t adesc = make_mnmajor_sw128_desc(sa, box_bytes);
+                    const int nkk = p.kp / 8;
+                    for (int kk = 0; kk < nkk; kk++) {
+                        for (int t = 0; t < tcount; t++) {
+                            uint64_t bdesc = make_mnmajor_sw128_desc(sb + t * nb2 * box_bytes, box_bytes);
+                            umma2_tf32(d_tmem + (uint32_t)(t * p.bn), adesc + (uint64_t)(kk * 64), bdesc + (uint64_t)(kk * 64), idesc,
+                                       (accum | kk) ? 1u : 0u);
+                        }
+                    }
+                    accum = 1;
+                    umma2_commit_mc(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit_mc(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const long ktot = (long)taps * p.Cin;
+        for (int u = cluster_id; u < units; u += nclusters) {
+            int g, cot, sp, cit, tg;
+            decode(u, g, cot, sp, cit, tg);
+            const int tap0 = tg * p.T;
+            const int tcount = taps - tap0 < p.T ? taps - tap0 : p.T;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int co = cot * 256 + (int)rank * 128 + row;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * WG_NCOLS);
+            for (int t = 0; t < tcount; t++) {
+                float* op = p.out + (((long)sp * p.G + g) * p.Cout + co) * ktot + (long)(tap0 + t) * p.Cin + cit * p.bn;
+                for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(t * p.bn + c0), v);
+                    float4* yp = reinterpret_cast<float4*>(op + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(leader_addr(smem_u32(&tempty_bar[acc])));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * WG_NCOLS));
+    }
+}
+
 __global__ void reduce_splits_tc_kernel(const float* __restrict__ part, float* __restrict__ out, long n4, int splits) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -1330,15 +1509,18 @@ static int wg_bn(int cin) {
 }
 
 static int wg_kp(const cg_conv_geom& g) { return ((long)g.B * g.Ho * g.Wo) % 64 == 0 ? 64 : 32; }
+// CTA pairs (256 output channels per unit) when the layer has them and every tap's N splits into two 32-channel-box halves
+static bool wg_pair(const cg_conv_geom& g) { return (g_pair_mode & 8) && g.Cout % 256 == 0 && wg_bn(g.Cin) % 64 == 0; }
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
     const int kp = wg_kp(g);
     int bn = wg_bn(g.Cin);
     int T = WG_NCOLS / bn;
     if (T > g.KH * g.KW) T = g.KH * g.KW;
-    long base = (long)g.G * ((g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
+    const bool pair = wg_pair(g);
+    long base = (long)g.G * (pair ? g.Cout / 256 : (g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
     init_driver();
-    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int sms = (g_sm_count > 0 ? g_sm_count : 148) / (pair ? 2 : 1);
     long maxs = Mpix / (kp * 8);  // at least 8 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
     if (maxs > 64) maxs = 64;
@@ -1423,6 +1605,34 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     p.out = p.splits == 1 ? dw : (float*)ws;
     p.T = WG_NCOLS / p.bn;
     if (p.T > g.KH * g.KW) p.T = g.KH * g.KW;
+    if (wg_pair(g)) {
+        int stage_bytes = p.kp * 128 * (4 + WG_NCOLS / 64);
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > 8) stages = 8;
+        p.stages = stages;
+        size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(wgrad_tc2_kernel): %s", cudaGetErrorString(e));
+                return CG_ERR_CUDA;
+            }
+            attr2_set = true;
+        }
+        long units = (long)g.G * (g.Cout / 256) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
+        int pairs = g_sm_count / 2;
+        int nclusters = (int)(units < pairs ? units : pairs);
+        if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_tc2: units=%ld splits=%d chunk=%ld stages=%d T=%d bn=%d kp=%d\n", units, p.splits, p.chunk, stages, p.T, p.bn, p.kp);
+        wgrad_tc2_kernel<<<2 * nclusters, TC_THREADS, smem, st>>>(p);
+        if (int rc = check_launch("wgrad_tc2_kernel")) return rc;
+        if (p.splits > 1) {
+            long n4 = (long)g.G * g.Cout * g.KH * g.KW * g.Cin / 4;
+            reduce_splits_tc_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float*)ws, dw, n4, p.splits);
+            return check_launch("reduce_splits_tc");
+        }
+        return CG_OK;
+    }
     int stage_bytes = p.kp * 128 * (4 + WG_NCOLS / 32);
     int stages = (200 * 1024) / stage_bytes;
     p.stages = stages;

@@ -29,6 +29,9 @@ CASES = [
     ('wgrad_3x3_c256_o256', 'wgrad', 2, 2, 2, 32, 32, 256, 256, 3, 1, 1),
     ('wgrad_4x4s2_c128_o256', 'wgrad', 2, 2, 2, 32, 32, 128, 256, 4, 2, 1),
     ('wgrad_4x4s2_c256_o512', 'wgrad', 2, 2, 4, 32, 32, 256, 512, 4, 2, 1),
+    ('wgrad_pair_c64_o256', 'wgrad', 2, 2, 2, 16, 16, 64, 256, 3, 1, 1),
+    ('wgrad_pair_c192_o256', 'wgrad', 1, 1, 2, 16, 16, 192, 256, 3, 1, 1),
+    ('wgrad_pair_1x1_c512_o512', 'wgrad', 3, 3, 4, 8, 8, 512, 512, 1, 1, 0),
     ('wgrad_shared_x', 'wgrad', 2, 1, 2, 16, 16, 64, 128, 3, 1, 1),
 ]
 
