@@ -1010,21 +1010,33 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
 // an im2col box with lower corner -padl, and an output written with stride s at offset ihf.
 // ------------------------------------------------------------------------------------------------
 // CinP >= Cin: rows ci >= Cin are zero (pads the 8 image lanes to the minimum UMMA N of 16)
-__global__ void dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, long total, int Cout, int Cin, int CinP,
-                                              int KH, int KW, int s) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+// 32 (co) x 32 (ci) tiles through shared memory: reads run along ci (contiguous in OHWI), writes along co (contiguous in the
+// transposed copy); grid = (co tiles x ci tiles, KH*KW, G)
+__global__ void __launch_bounds__(256) dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin,
+                                                                     int CinP, int KH, int KW, int s) {
+    __shared__ float tile[32][33];
     const int TH = KH / s, TW = KW / s;
-    int co = (int)(i % Cout);
-    long t = i / Cout;
-    int ss = (int)(t % TW); t /= TW;
-    int r = (int)(t % TH); t /= TH;
-    int ci = (int)(t % CinP); t /= CinP;
-    int cls = (int)(t % (s * s));
-    int g = (int)(t / (s * s));
-    int ph = cls / s, pw = cls - ph * s;
-    int kh = ph + s * (TH - 1 - r), kw = pw + s * (TW - 1 - ss);
-    wt[i] = ci < Cin ? __ldg(w + ((((long)g * Cout + co) * KH + kh) * KW + kw) * Cin + ci) : 0.f;
+    const int cit = (CinP + 31) / 32;
+    const int co0 = (blockIdx.x / cit) * 32, ci0 = (blockIdx.x % cit) * 32;
+    int t = blockIdx.y;
+    const int ss = t % TW; t /= TW;
+    const int r = t % TH; t /= TH;
+    const int cls = t;
+    const int g = blockIdx.z;
+    const int ph = cls / s, pw = cls - ph * s;
+    const int kh = ph + s * (TH - 1 - r), kw = pw + s * (TW - 1 - ss);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+        tile[ty + 8 * j][tx] = (co < Cout && ci < Cin) ? __ldg(w + ((((long)g * Cout + co) * KH + kh) * KW + kw) * Cin + ci) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int ci = ci0 + ty + 8 * j, co = co0 + tx;
+        if (ci < CinP && co < Cout) wt[(((((long)g * s * s + cls) * CinP + ci) * TH + r) * TW + ss) * Cout + co] = tile[tx][ty + 8 * j];
+    }
 }
 
 bool tc_dgrad_supported(const cg_conv_geom& g) {
@@ -1062,7 +1074,9 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
     size_t wt_bytes = ((size_t)g.G * g.Cout * g.KH * g.KW * CinP * sizeof(float) + 1023) & ~(size_t)1023;
     float* d_seen = g.ups ? (float*)((uint8_t*)ws + wt_bytes) : dx;
     long total = (long)g.G * g.Cout * g.KH * g.KW * CinP;
-    dgrad_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wt, total, g.Cout, g.Cin, CinP, g.KH, g.KW, s);
+    (void)total;
+    dgrad_weight_transform_kernel<<<dim3(cdiv(g.Cout, 32) * cdiv(CinP, 32), g.KH * g.KW, g.G), dim3(32, 8), 0, st>>>(w, wt, g.Cout, g.Cin, CinP,
+                                                                                                                  g.KH, g.KW, s);
     if (int rc = check_launch("dgrad_weight_transform")) return rc;
 
     TcParams p{};

@@ -62,15 +62,34 @@ __global__ void __launch_bounds__(256) in_stats_partial_kernel(const float* __re
         o[0] = s.x; o[1] = q.x; o[2] = s.y; o[3] = q.y; o[4] = s.z; o[5] = q.z; o[6] = s.w; o[7] = q.w;
     }
 }
-__global__ void in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
-                                      long GBC, int nchunks, int HW, float eps) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= GBC) return;
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nchunks; k++) {
-        s += (double)part[((long)k * GBC + i) * 2];
-        q += (double)part[((long)k * GBC + i) * 2 + 1];
+// 32 items x 8 chunk slices per block: the chunk loop of one (gb, c) item is split eight ways and folded in shared memory
+// (fp64), so the 256x256 maps (512 chunks, only 2048 items) do not serialise 512 dependent loads per thread.
+constexpr int FIN_ITEMS = 32, FIN_SLICES = 8;
+__device__ __forceinline__ bool final_sums(const float* __restrict__ part, long GBC, int nchunks, long i, double& s, double& q) {
+    __shared__ double sm[2][FIN_SLICES][FIN_ITEMS];
+    s = 0.0; q = 0.0;
+    if (i < GBC)
+        for (int k = threadIdx.y; k < nchunks; k += FIN_SLICES) {
+            float2 v = __ldg(reinterpret_cast<const float2*>(part + ((long)k * GBC + i) * 2));
+            s += (double)v.x;
+            q += (double)v.y;
+        }
+    sm[0][threadIdx.y][threadIdx.x] = s;
+    sm[1][threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y != 0 || i >= GBC) return false;
+    for (int k = 1; k < FIN_SLICES; k++) {
+        s += sm[0][k][threadIdx.x];
+        q += sm[1][k][threadIdx.x];
     }
+    return true;
+}
+__global__ void __launch_bounds__(FIN_ITEMS * FIN_SLICES) in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ mean,
+                                                                                 float* __restrict__ rstd, long GBC, int nchunks, int HW,
+                                                                                 float eps) {
+    long i = (long)blockIdx.x * FIN_ITEMS + threadIdx.x;
+    double s, q;
+    if (!final_sums(part, GBC, nchunks, i, s, q)) return;
     double m = s / HW;
     double var = q / HW - m * m;
     if (var < 0.0) var = 0.0;
@@ -210,16 +229,13 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(NormP p) {
     }
 }
 // sums[gb][C][2] (fp32) = chunk totals; also scatters d_beta / d_gamma into d_adain
-__global__ void norm_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ sums, float* __restrict__ d_adain,
-                                      int GB, int C, int P, int off, int nchunks) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(FIN_ITEMS * FIN_SLICES) norm_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ sums,
+                                                                                 float* __restrict__ d_adain, int GB, int C, int P, int off,
+                                                                                 int nchunks) {
+    long i = (long)blockIdx.x * FIN_ITEMS + threadIdx.x;
     long GBC = (long)GB * C;
-    if (i >= GBC) return;
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nchunks; k++) {
-        s += (double)part[((long)k * GBC + i) * 2];
-        q += (double)part[((long)k * GBC + i) * 2 + 1];
-    }
+    double s, q;
+    if (!final_sums(part, GBC, nchunks, i, s, q)) return;
     sums[i * 2] = (float)s;
     sums[i * 2 + 1] = (float)q;
     if (d_adain) {
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormP p, const floa
 }
 
 int in_stats_finalize(const float* part, float* mean, float* rstd, long GBC, int nchunks, int HW, float eps, cudaStream_t st) {
-    in_stats_final_kernel<<<cdiv(GBC, 256), 256, 0, st>>>(part, mean, rstd, GBC, nchunks, HW, eps);
+    in_stats_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>(part, mean, rstd, GBC, nchunks, HW, eps);
     return check_launch("in_stats_final");
 }
 
@@ -302,7 +318,7 @@ extern "C" int cg_in_stats(const float* y, float* mean, float* rstd, int G, int 
     in_stats_partial_kernel<<<dim3(nchunks, G * B), 256, 0, st>>>(y, (float*)ws, HW, C);
     if (int rc = check_launch("in_stats_partial")) return rc;
     long GBC = (long)G * B * C;
-    in_stats_final_kernel<<<cdiv(GBC, 256), 256, 0, st>>>((const float*)ws, mean, rstd, GBC, nchunks, HW, eps);
+    in_stats_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>((const float*)ws, mean, rstd, GBC, nchunks, HW, eps);
     return check_launch("in_stats_final");
 }
 
@@ -339,7 +355,8 @@ extern "C" int cg_norm_act_bwd(const float* dz, const float* y, const float* mea
     dim3 grid(nchunks, G * B);
     norm_bwd_partial_kernel<<<grid, 256, 0, st>>>(p);
     if (int rc = check_launch("norm_bwd_partial")) return rc;
-    norm_bwd_final_kernel<<<cdiv(GBC, 256), 256, 0, st>>>(p.part, sums, adain ? d_adain : nullptr, G * B, C, P, off, nchunks);
+    norm_bwd_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>(p.part, sums, adain ? d_adain : nullptr, G * B, C, P, off,
+                                                                                       nchunks);
     if (int rc = check_launch("norm_bwd_final")) return rc;
     norm_bwd_apply_kernel<<<grid, 256, 0, st>>>(p, sums);
     return check_launch("norm_bwd_apply");
