@@ -14,6 +14,7 @@ extern std::atomic<uint64_t> g_launches;
 extern int g_tc_mode;
 extern int g_pair_mode;
 extern int g_pair_cap;
+extern int g_wgrad_xm;
 
 inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -41,6 +41,7 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static int g_sm_count = 0;
 int g_pair_cap = 0;
+int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
 int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
                       // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
 static int g_driver_version = 0;
@@ -1133,6 +1134,7 @@ struct WgParams {
     int G, xg_images, B, P, Q, Cin, Cout, KH, KW, stride, pad, bn, splits, stages;
     int kp;            // pixels per pipeline stage: 64 when the pixel count allows (fewer, larger TMA boxes), else 32
     int T;             // filter taps accumulated per work unit (they share the dy tile): T * bn <= 256
+    int Tm;            // (x-on-M variant) 128-row tiles of (tap, 32-channel block) rows per work unit: Tm * Cout <= 256
     long Mpix, chunk;  // pixels per group; pixels per split (multiple of WG_KP)
     float* out;        // [splits][G][Cout][KH*KW][Cin]
 };
@@ -1505,6 +1507,184 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad
     }
 }
 
+// Weight gradient with the roles swapped, for layers with <= 64 output channels: the 128 MMA rows are four (tap, 32-channel
+// block) row groups of x instead of output channels (which would leave half of every M = 128 instruction empty), dy is the N
+// operand (N = Cout).  D[(tap, ci)][co] is written back transposed: for a fixed co the 32 lanes of a warp hold 32
+// consecutive ci = one 128-byte store.  Up to Tm row tiles share the dy stage.
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_xm_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int box_bytes = p.kp * 128;
+    const int nbo = p.Cout / 32;                  // dy boxes (1 or 2)
+    const int a_bytes = 2 * box_bytes;            // dy slot (N operand)
+    const int b_bytes = p.Tm * 4 * box_bytes;     // x row groups (M operand)
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tfull_bar = empty_bar + p.stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int CB = p.Cin / 32;                    // 32-channel blocks per tap
+    const int RG = p.KH * p.KW * CB;              // row groups in all
+    const int GPU_ = p.Tm * 4;                    // row groups per unit
+    const int MG = (RG + GPU_ - 1) / GPU_;
+    const int units = p.G * p.splits * MG;
+    const int tmem_cols = 2 * WG_NCOLS;
+
+    if (warp == TC_PRODUCER_WARP && lane == 0) {
+        prefetch_tmap(&p.amap);
+        prefetch_tmap(&p.bmap);
+    }
+    if (warp == TC_MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; s++) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int a = 0; a < 2; a++) {
+                mbar_init(&tfull_bar[a], 1);
+                mbar_init(&tempty_bar[a], 128);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // unit -> (g, split, row-tile group), row-tile group fastest so CTAs running together share the dy tile in L2
+    auto decode = [&](int u, int& g, int& sp, int& mg) {
+        mg = u % MG; u /= MG;
+        sp = u % p.splits;
+        g = u / p.splits;
+    };
+
+    if (warp == TC_PRODUCER_WARP) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int g, sp, mg;
+            decode(u, g, sp, mg);
+            const int rg0 = mg * GPU_;
+            const int ng = RG - rg0 < GPU_ ? RG - rg0 : GPU_;  // row groups of this unit
+            const long mbeg = (long)sp * p.chunk;
+            const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
+            // lane roles: 0..nbo-1 -> dy boxes; 2..2+ng -> x row groups (tap, channel block)
+            const int q = lane - 2;
+            const bool is_a = lane < nbo;
+            const bool is_b = q >= 0 && q < ng;
+            const int rg = is_b ? rg0 + q : 0;
+            const int tap = rg / CB, cb = rg - tap * CB;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const uint32_t tx = (uint32_t)((nbo + ng) * box_bytes);
+            for (long m = mbeg; m < mend; m += p.kp) {
+                int img = (int)(m / (p.P * p.Q));
+                int rem = (int)(m - (long)img * p.P * p.Q);
+                int pp = rem / p.Q, qq = rem - pp * p.Q;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                if (lane == 0) mbar_expect_tx(&full_bar[stage], tx);
+                __syncwarp();
+                if (is_a) tma_load_2d(&p.amap, &full_bar[stage], sa + lane * box_bytes, lane * 32, (int)((long)g * p.Mpix + m));
+                if (is_b)
+                    tma_load_im2col_4d(&p.bmap, &full_bar[stage], sb + q * box_bytes, cb * 32, -p.pad + qq * p.stride, -p.pad + pp * p.stride,
+                                       g * p.xg_images + img, (uint16_t)kw, (uint16_t)kh);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        if (lane == 0) {
+            // kind::tf32, D=F32, A (x) and B (dy) MN-major (bits 15, 16), M=128, N=Cout
+            const uint32_t idesc = make_idesc_tf32(p.Cout) | (1u << 15) | (1u << 16);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                int g, sp, mg;
+                decode(u, g, sp, mg);
+                const int rg0 = mg * GPU_;
+                const int ng = RG - rg0 < GPU_ ? RG - rg0 : GPU_;
+                const int ntile = (ng + 3) >> 2;
+                const long mbeg = (long)sp * p.chunk;
+                const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_NCOLS);
+                uint32_t accum = 0;
+                for (long m = mbeg; m < mend; m += p.kp) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    uint32_t sb = sa + a_bytes;
+                    uint64_t ndesc = make_mnmajor_sw128_desc(sa, box_bytes);  // dy: N operand
+                    const int nkk = p.kp / 8;
+                    for (int kk = 0; kk < nkk; kk++) {
+                        for (int t = 0; t < ntile; t++) {
+                            // a partial last tile multiplies stale shared memory in its missing row groups: those D rows are never stored
+                            uint64_t mdesc = make_mnmajor_sw128_desc(sb + t * 4 * box_bytes, box_bytes);
+                            umma_tf32(d_tmem + (uint32_t)(t * p.Cout), mdesc + (uint64_t)(kk * 64), ndesc + (uint64_t)(kk * 64), idesc,
+                                      (accum | kk) ? 1u : 0u);
+                        }
+                    }
+                    accum = 1;
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const long ktot = (long)p.KH * p.KW * p.Cin;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int g, sp, mg;
+            decode(u, g, sp, mg);
+            const int rg0 = mg * GPU_;
+            const int ng = RG - rg0 < GPU_ ? RG - rg0 : GPU_;
+            const int ntile = (ng + 3) >> 2;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * WG_NCOLS);
+            for (int t = 0; t < ntile; t++) {
+                const int q = t * 4 + quad;          // this warp's row group inside the unit
+                const bool valid = q < ng;
+                const int rg = rg0 + q;
+                const int tap = rg / CB, cb = rg - tap * CB;
+                // dw[sp][g][co][tap][ci], ci = cb*32 + lane: one 128-byte store per output channel
+                float* op = p.out + ((long)sp * p.G + g) * p.Cout * ktot + (long)tap * p.Cin + cb * 32 + lane;
+                for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(t * p.Cout + c0), v);
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) op[(long)(c0 + j) * ktot] = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
 __global__ void reduce_splits_tc_kernel(const float* __restrict__ part, float* __restrict__ out, long n4, int splits) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -1525,6 +1705,15 @@ static int wg_bn(int cin) {
 static int wg_kp(const cg_conv_geom& g) { return ((long)g.B * g.Ho * g.Wo) % 64 == 0 ? 64 : 32; }
 // CTA pairs (256 output channels per unit) when the layer has them and every tap's N splits into two 32-channel-box halves
 static bool wg_pair(const cg_conv_geom& g) { return (g_pair_mode & 8) && g.Cout % 256 == 0 && wg_bn(g.Cin) % 64 == 0; }
+// x-on-M variant for <= 64 output channels (a 128-row cout tile would be half empty)
+static bool wg_xm(const cg_conv_geom& g) { return g_wgrad_xm && (g.Cout == 64 || g.Cout == 32) && g.Cin % 32 == 0; }
+static int wg_xm_tm(const cg_conv_geom& g) {
+    int rg = g.KH * g.KW * (g.Cin / 32), mt = (rg + 3) / 4;
+    int tm = WG_NCOLS / g.Cout;  // TMEM columns
+    if (tm > 2) tm = 2;          // 2 dy + 8 x boxes per 64-pixel stage = 80 KB, two stages (three tiles = 112 KB would leave one)
+    if (tm > mt) tm = mt;
+    return tm;
+}
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
     const int kp = wg_kp(g);
@@ -1533,6 +1722,11 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     if (T > g.KH * g.KW) T = g.KH * g.KW;
     const bool pair = wg_pair(g);
     long base = (long)g.G * (pair ? g.Cout / 256 : (g.Cout + 127) / 128) * (g.Cin / bn) * ((g.KH * g.KW + T - 1) / T);
+    if (wg_xm(g)) {
+        int tm = wg_xm_tm(g);
+        int rgs = g.KH * g.KW * (g.Cin / 32);
+        base = (long)g.G * ((rgs + tm * 4 - 1) / (tm * 4));
+    }
     init_driver();
     const int sms = (g_sm_count > 0 ? g_sm_count : 148) / (pair ? 2 : 1);
     long maxs = Mpix / (kp * 8);  // at least 8 pipeline stages of work per split
@@ -1619,6 +1813,35 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     p.out = p.splits == 1 ? dw : (float*)ws;
     p.T = WG_NCOLS / p.bn;
     if (p.T > g.KH * g.KW) p.T = g.KH * g.KW;
+    if (wg_xm(g)) {
+        p.Tm = wg_xm_tm(g);
+        int stage_bytes = p.kp * 128 * (2 + 4 * p.Tm);
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > 8) stages = 8;
+        p.stages = stages;
+        size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+        static bool attr3_set = false;
+        if (!attr3_set) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_xm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(wgrad_xm_kernel): %s", cudaGetErrorString(e));
+                return CG_ERR_CUDA;
+            }
+            attr3_set = true;
+        }
+        int rgs = g.KH * g.KW * (g.Cin / 32);
+        long units = (long)g.G * p.splits * ((rgs + p.Tm * 4 - 1) / (p.Tm * 4));
+        int grid = (int)(units < g_sm_count ? units : g_sm_count);
+        if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_xm: units=%ld splits=%d chunk=%ld stages=%d Tm=%d kp=%d\n", units, p.splits, p.chunk, stages, p.Tm, p.kp);
+        wgrad_xm_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+        if (int rc = check_launch("wgrad_xm_kernel")) return rc;
+        if (p.splits > 1) {
+            long n4 = (long)g.G * g.Cout * g.KH * g.KW * g.Cin / 4;
+            reduce_splits_tc_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float*)ws, dw, n4, p.splits);
+            return check_launch("reduce_splits_tc");
+        }
+        return CG_OK;
+    }
     if (wg_pair(g)) {
         int stage_bytes = p.kp * 128 * (4 + WG_NCOLS / 64);
         int stages = (200 * 1024) / stage_bytes;

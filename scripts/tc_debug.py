@@ -32,6 +32,9 @@ CASES = [
     ('wgrad_pair_c64_o256', 'wgrad', 2, 2, 2, 16, 16, 64, 256, 3, 1, 1),
     ('wgrad_pair_c192_o256', 'wgrad', 1, 1, 2, 16, 16, 192, 256, 3, 1, 1),
     ('wgrad_pair_1x1_c512_o512', 'wgrad', 3, 3, 4, 8, 8, 512, 512, 1, 1, 0),
+    ('wgrad_xm_3x3_c128_o64', 'wgrad', 2, 2, 2, 16, 16, 128, 64, 3, 1, 1),
+    ('wgrad_xm_4x4s2_c32_o64', 'wgrad', 2, 2, 2, 32, 32, 32, 64, 4, 2, 1),
+    ('wgrad_xm_1x1_c96_o64', 'wgrad', 2, 1, 2, 16, 16, 96, 64, 1, 1, 0),
     ('wgrad_shared_x', 'wgrad', 2, 1, 2, 16, 16, 64, 128, 3, 1, 1),
 ]
 

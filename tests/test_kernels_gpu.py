@@ -71,6 +71,10 @@ CONV_CASES = [
     # CTA-pair weight gradient: 256 output channels per unit; 64- and 192-channel inputs (one / three boxes per CTA and tap)
     ('tc_pair_wgrad_c64_o256', 2, 2, 2, 16, 16, 64, 256, 3, 1, 1, False),
     ('tc_pair_wgrad_c192_o256', 1, 1, 2, 16, 16, 192, 256, 3, 1, 1, False),
+    # x-on-M weight gradient (<= 64 output channels): partial last row tile (3x3x64: 18 row groups), 1x1 with 3 row groups
+    ('tc_xm_wgrad_c128_o64', 2, 2, 2, 16, 16, 128, 64, 3, 1, 1, False),
+    ('tc_xm_wgrad_1x1_c96_o64', 2, 1, 2, 16, 16, 96, 64, 1, 1, 0, False),
+    ('tc_xm_wgrad_4x4s2_c32_o32', 2, 2, 2, 32, 32, 32, 32, 4, 2, 1, False),
     # image-side layers on the explicit-patch path (im2col -> 1x1 tensor-core GEMM)
     ('patch_disc0_3x3_pair', 2, 2, 2, 16, 16, 8, 64, 3, 1, 1, False),
     ('patch_dis0_4x4s2_img', 2, 2, 4, 16, 16, 4, 64, 4, 2, 1, False),
