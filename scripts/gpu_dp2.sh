@@ -2,7 +2,7 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi -L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
 echo "bench n2 rc=$?"; cut -c1-900 gpurun_out/bench_n2.json; tail -8 gpurun_out/bench_n2.err
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/dp_check.py > gpurun_out/dp_check.log 2>&1
 echo "dp check rc=$?"; tail -12 gpurun_out/dp_check.log
