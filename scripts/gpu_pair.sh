@@ -1,5 +1,5 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-COUNCIL_DEBUG=1 TC_ONLY=wgrad timeout 600 python scripts/tc_debug.py > gpurun_out/tc_debug.log 2>&1
-cut -c1-260 gpurun_out/tc_debug.log
+timeout 300 python scripts/prof_wgrad_pair.py > gpurun_out/prof_wgrad_km.log 2>&1
+tail -5 gpurun_out/prof_wgrad_km.log

@@ -32,4 +32,4 @@ for (G, B, H, W, Cin, Cout, K, s, pad) in CASES[:1] if one else CASES:
         ops.conv_wgrad(x, dy, dw, None, s, pad)
         torch.cuda.synchronize()
         break
-    print((G, B, H, W, Cin, Cout, K, s), 'single ms %.4f' % timeit(7 | 64), 'pair ms %.4f' % timeit(7))
+    print((G, B, H, W, Cin, Cout, K, s), 'single ms %.4f' % timeit(7), 'pair ms %.4f' % timeit(7 | 64))

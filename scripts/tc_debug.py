@@ -62,7 +62,7 @@ def run_case(idx):
     elif kind == 'wgrad':
         Ho = (H + 2 * pad - K) // stride + 1
         dy = torch.randn(G, B, Ho, Ho * W // H, Cout, generator=g).cuda()
-        ops.set_tensor_core_mode(1)
+        ops.set_tensor_core_mode(int(os.environ.get('TC_MODE', '1')))
         y = torch.zeros_like(w)
         ops.conv_wgrad(x, dy, y, None, stride, pad)
         torch.cuda.synchronize()
@@ -101,8 +101,10 @@ if __name__ == '__main__':
         for i, c in enumerate(CASES):
             if only and c[1] not in only.split(','):
                 continue
+            if os.environ.get('TC_NAME') and os.environ['TC_NAME'] not in c[0]:
+                continue
             try:
-                r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=45)
+                r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=int(os.environ.get('TC_TIMEOUT', '45')))
                 lines = [l for l in r.stdout.splitlines() if l.startswith('RESULT')]
                 print(c[0], lines[0] if lines else 'NO RESULT rc=%d %s' % (r.returncode, (r.stderr or '')[-600:]), flush=True)
             except subprocess.TimeoutExpired:
