@@ -244,6 +244,18 @@ def main():
     except Exception:
         pass
     roofline = None
+    roofline_hbm = None
+    hbm_times = {k: v for k, v in (ktimes or {}).items() if k.startswith('hbm:')}
+    ktimes = {k: v for k, v in (ktimes or {}).items() if not k.startswith('hbm:')}
+    if hbm_times:
+        # the largest HBM-bound kernel group of the step: algorithmic bytes / measured launch time vs the measured copy bandwidth
+        hkey, (h_ms, h_cnt, h_bytes) = max(hbm_times.items(), key=lambda kv: kv[1][0])
+        hbm_peak = peaks.get('hbm_gbs', 6500.0)
+        h_ach = h_bytes / (h_ms / h_cnt * 1e-3) / 1e9
+        roofline_hbm = {'bound': 'hbm', 'kernel': hkey[4:], 'achieved': h_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': h_ach / hbm_peak,
+                        'bytes_per_launch': h_bytes, 'launches': h_cnt, 'avg_ms': h_ms / h_cnt, 'share_of_step': h_ms / ms,
+                        'all_hbm_kernels_ms_per_step': round(sum(v[0] for v in hbm_times.values()) / args.steps, 3),
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth)' if peaks else 'fallback 6500'}
     if ktimes:
         key, (tot_ms, cnt, flops) = max(ktimes.items(), key=lambda kv: kv[1][0])
         tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2.0  # TF32 runs at half the bf16 tensor rate
@@ -261,10 +273,12 @@ def main():
     line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'tf32' if args.tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
-            'gpu_launches': int(launches), 'roofline': roofline,
+            'gpu_launches': int(launches), 'roofline': roofline, 'roofline_hbm': roofline_hbm,
             'step_algorithmic_tflops': alg_tflop / (ms_per_step * 1e-3) / world,
             'kernel_times_ms_per_step': ({k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:60]}
                                          if ktimes else None),
+            'hbm_kernel_times_ms_per_step': ({k[4:]: round(v[0] / args.steps, 3) for k, v in sorted(hbm_times.items(), key=lambda kv: -kv[1][0])[:20]}
+                                             if hbm_times else None),
             'losses': {'gen': [float(v) for v in trainer.loss_gen_total_s], 'dis': [float(v) for v in trainer.loss_dis_total_s]}}
     if not args.no_cpu_baseline:
         rate, dt, cores = cpu_oracle_rate(args.workload, 1, 1)

@@ -132,7 +132,7 @@ class CudaOps:
         self._timing = {}
 
     def stop_timing(self):
-        """-> {kernel key: (total ms, launches, algorithmic FLOPs per launch)} for the timed conv launches."""
+        """-> {kernel key: (total ms, launches, algorithmic FLOPs (conv_*) or HBM bytes (hbm:*) per launch)}."""
         rec, self._timing = self._timing or {}, None
         torch.cuda.synchronize(self.device)
         return {k: (sum(a.elapsed_time(b) for a, b in evs), len(evs), fl) for k, (evs, fl) in rec.items()}
@@ -143,11 +143,17 @@ class CudaOps:
         key = '%s G%d B%d %dx%d Cin%d Cout%d k%d s%d%s' % (kind, g.G, g.B, g.H, g.W, g.Cin, g.Cout, g.KH, g.stride,
                                                           ' ups' if g.ups else '')
         flops = 2.0 * g.G * g.B * g.Ho * g.Wo * g.Cout * g.KH * g.KW * g.Cin
+        return self._timed_raw(key, flops, fn)
+
+    def _timed_raw(self, key, work, fn):
+        """work = algorithmic FLOPs (conv_* keys) or algorithmic HBM bytes (hbm:* keys) of one launch."""
+        if self._timing is None:
+            return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = fn()
         e1.record()
-        self._timing.setdefault(key, ([], flops))[0].append((e0, e1))
+        self._timing.setdefault(key, ([], work))[0].append((e0, e1))
         return out
 
     @staticmethod
@@ -211,8 +217,9 @@ class CudaOps:
         G, B, H, W, Cc = y.shape
         mean, rstd = self.empty(G, B, Cc), self.empty(G, B, Cc)
         ws = self._ws_for(((H * W + 127) // 128) * G * B * Cc * 8)
-        self._ck(self.lib.cg_in_stats(_p(y), _p(mean), _p(rstd), G, B, H * W, Cc, eps, _p(ws), ws.numel(),
-                                      self._stream()), 'cg_in_stats')
+        self._timed_raw('hbm:in_stats G%d B%d %dx%d C%d' % (G, B, H, W, Cc), 4.0 * y.numel(),
+                        lambda: self._ck(self.lib.cg_in_stats(_p(y), _p(mean), _p(rstd), G, B, H * W, Cc, eps, _p(ws), ws.numel(),
+                                                              self._stream()), 'cg_in_stats'))
         return mean, rstd
 
     def norm_act_fwd(self, y, mean, rstd, adain=None, off=0, res=None, act=ACT_NONE, ups=False):
@@ -220,8 +227,11 @@ class CudaOps:
         G, B, H, W, Cc = y.shape
         z = self.empty(G, B, 2 * H if ups else H, 2 * W if ups else W, Cc)
         P = adain.shape[-1] if adain is not None else 0
-        self._ck(self.lib.cg_norm_act_fwd(_p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(res), _p(z), G, B, H, W, Cc,
-                                          act, int(bool(ups)), self._stream()), 'cg_norm_act_fwd')
+        units = 1 + (1 if res is not None else 0) + (4 if ups else 1)  # read y (+ residual), write z (x4 when upsampling)
+        self._timed_raw('hbm:norm_act_fwd G%d B%d %dx%d C%d%s%s' % (G, B, H, W, Cc, ' res' if res is not None else '', ' ups' if ups else ''),
+                        4.0 * units * y.numel(),
+                        lambda: self._ck(self.lib.cg_norm_act_fwd(_p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(res), _p(z), G, B, H, W,
+                                                                  Cc, act, int(bool(ups)), self._stream()), 'cg_norm_act_fwd'))
         return z
 
     def norm_act_bwd(self, dz, y, mean, rstd, adain=None, off=0, act=ACT_NONE, ups=False, d_adain=None):
@@ -230,9 +240,11 @@ class CudaOps:
         dy = self.empty(G, B, H, W, Cc)
         P = adain.shape[-1] if adain is not None else 0
         ws = self._ws_for((((H * W + 127) // 128) + 1) * G * B * Cc * 8)
-        self._ck(self.lib.cg_norm_act_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
-                                          G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
-                 'cg_norm_act_bwd')
+        units = 2 * (1 + (4 if ups else 1)) + 1  # two passes over (y, dz) -- the reduction, then the apply -- and one write of dy
+        self._timed_raw('hbm:norm_act_bwd G%d B%d %dx%d C%d%s' % (G, B, H, W, Cc, ' ups' if ups else ''), 4.0 * units * y.numel(),
+                        lambda: self._ck(self.lib.cg_norm_act_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
+                                                                  G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
+                                         'cg_norm_act_bwd'))
         return dy
 
     def upsample2x_bwd(self, d_up):
