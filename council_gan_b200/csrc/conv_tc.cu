@@ -19,6 +19,13 @@
 // flipped copy of the weights, and (for stride-2 layers) one launch "class" per output parity with its
 // own im2col bounding box and a strided output mapping (see tc_conv_dgrad).
 //
+// Kernels in this file (host dispatch at the bottom of each section):
+//   conv_tc_kernel<32|8>  forward / data gradient, one CTA per SM (tcgen05.mma.cta_group::1)
+//   conv_tc2_kernel       the same for 128/256-wide tiles as CTA pairs (cta_group::2, M = 256 over two SMs)
+//   wgrad_tc_kernel       weight gradient, cout on M, MN-major operands straight from the NHWC tensors
+//   wgrad_xm_kernel       weight gradient with x on M for <= 64 output channels
+//   wgrad_tc2_kernel      CTA-pair weight gradient (measured slower; behind a cg_set_tensor_core_mode switch)
+//
 // Reference call sites replaced: nn.Conv2d forward (networks.py:513,516) and cuDNN dgrad via autograd.
 #include "common.cuh"
 #include <cstdlib>
