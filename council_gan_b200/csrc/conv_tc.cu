@@ -49,6 +49,8 @@ static EncodeIm2colFn g_encode_im2col = nullptr;
 static int g_sm_count = 0;
 int g_pair_cap = 0;
 int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
+int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
+int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
 int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
                       // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
 static int g_driver_version = 0;
@@ -244,7 +246,7 @@ struct TcParams {
 };
 
 template <int BK>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -849,7 +851,9 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     p.cps = cps;
     int stage_bytes = cps * chunk_bytes;
     const int stat_bytes = p.stats ? 4 * 32 * 36 * 4 : 0;
-    int stages = (226 * 1024 - 1024 - 512 - stat_bytes) / stage_bytes;  // 227 KB dynamic shared memory per CTA
+    // narrow tiles are bound by the single MMA-issuing thread's per-stage latency: two co-resident CTAs per SM interleave their MMAs
+    const bool two = g_fwd_2cta && p.bn <= 64 && !p.stats && 2 * stage_bytes <= 100 * 1024;
+    int stages = ((two ? 104 : 226) * 1024 - 1024 - 512 - stat_bytes) / stage_bytes;  // 227 KB dynamic shared memory per SM
     if (stages > 12) stages = 12;
     if (stages > 4 && stage_bytes >= 48 * 1024) stages = 4;
     if (p.n_store == 0) p.n_store = p.bn;
@@ -913,7 +917,8 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
         conv_tc2_kernel<<<2 * nclusters, TC_THREADS, smem2, st>>>(p);
         return check_launch("conv_tc2_kernel");
     }
-    int grid = (int)(tiles < g_sm_count ? tiles : g_sm_count);
+    const long slots = (long)g_sm_count * (two ? 2 : 1);
+    int grid = (int)(tiles < slots ? tiles : slots);
     if (p.bk == 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(p);
     else conv_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(p);
     return check_launch("conv_tc_kernel");
@@ -1141,6 +1146,7 @@ struct WgParams {
     int G, xg_images, B, P, Q, Cin, Cout, KH, KW, stride, pad, bn, splits, stages;
     int kp;            // pixels per pipeline stage: 64 when the pixel count allows (fewer, larger TMA boxes), else 32
     int T;             // filter taps accumulated per work unit (they share the dy tile): T * bn <= 256
+    int nacc;          // TMEM accumulator stages: 2 (one CTA per SM) or 1 (two co-resident CTAs per SM share the 512 columns)
     int Tm;            // (x-on-M variant) 128-row tiles of (tap, 32-channel block) rows per work unit: Tm * Cout <= 256
     long Mpix, chunk;  // pixels per group; pixels per split (multiple of WG_KP)
     float* out;        // [splits][G][Cout][KH*KW][Cin]
@@ -1161,7 +1167,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1181,7 +1187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int COT = (p.Cout + 127) / 128;
     const int CIT = p.Cin / p.bn;
     const int units = p.G * COT * p.splits * CIT * TG;
-    const int tmem_cols = 2 * WG_NCOLS;
+    const int tmem_cols = p.nacc * WG_NCOLS;
 
     if (warp == TC_PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&p.amap);
@@ -1292,7 +1298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -1325,7 +1331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -1709,7 +1715,6 @@ static int wg_bn(int cin) {
     return 0;
 }
 
-static int wg_kp(const cg_conv_geom& g) { return ((long)g.B * g.Ho * g.Wo) % 64 == 0 ? 64 : 32; }
 // CTA pairs (256 output channels per unit) when the layer has them and every tap's N splits into two 32-channel-box halves
 static bool wg_pair(const cg_conv_geom& g) { return (g_pair_mode & 8) && g.Cout % 256 == 0 && wg_bn(g.Cin) % 64 == 0; }
 // x-on-M variant for <= 64 output channels (a 128-row cout tile would be half empty)
@@ -1721,6 +1726,9 @@ static int wg_xm_tm(const cg_conv_geom& g) {
     if (tm > mt) tm = mt;
     return tm;
 }
+// 64-pixel stages (fewer, larger TMA boxes) for the one-CTA-per-SM kernels; the plain kernel runs two CTAs per SM with 32-pixel stages
+static bool wg_two(const cg_conv_geom& g) { return g_wgrad_2cta && !wg_pair(g) && !wg_xm(g); }
+static int wg_kp(const cg_conv_geom& g) { return (!wg_two(g) && ((long)g.B * g.Ho * g.Wo) % 64 == 0) ? 64 : 32; }
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
     const int kp = wg_kp(g);
@@ -1735,7 +1743,7 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
         base = (long)g.G * ((rgs + tm * 4 - 1) / (tm * 4));
     }
     init_driver();
-    const int sms = (g_sm_count > 0 ? g_sm_count : 148) / (pair ? 2 : 1);
+    const int sms = (g_sm_count > 0 ? g_sm_count : 148) * (wg_two(g) ? 2 : 1) / (pair ? 2 : 1);
     long maxs = Mpix / (kp * 8);  // at least 8 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
     if (maxs > 64) maxs = 64;
@@ -1877,8 +1885,12 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         }
         return CG_OK;
     }
+    // two co-resident CTAs per SM (g_wgrad_2cta): 32-pixel stages, two per CTA, one TMEM accumulator stage each -- the MMAs of two
+    // independent units interleave on the tensor pipe
+    const bool two = wg_two(g);
+    p.nacc = two ? 1 : 2;
     int stage_bytes = p.kp * 128 * (4 + WG_NCOLS / 32);
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = ((two ? 100 : 200) * 1024) / stage_bytes;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
     static bool attr_set = false;
@@ -1891,7 +1903,8 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         attr_set = true;
     }
     long units = (long)g.G * ((g.Cout + 127) / 128) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
-    int grid = (int)(units < g_sm_count ? units : g_sm_count);
+    const int slots = g_sm_count * (two ? 2 : 1);
+    int grid = (int)(units < slots ? units : slots);
     wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
     if (int rc = check_launch("wgrad_tc_kernel")) return rc;
     if (p.splits > 1) {

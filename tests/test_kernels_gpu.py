@@ -83,13 +83,14 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64])
+@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64 | (1 << 16), 7 | (1 << 17)])
 def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
-    """tc = 0: SIMT fp32; 1: the default tensor-core dispatch; 7|32|64: additionally the CTA-pair (cta_group::2) variants that are
-    off by default because they measured slower (64-wide forward tiles, weight gradient) -- kept correct for round 2."""
+    """tc = 0: SIMT fp32; 1: the default tensor-core dispatch; 7|32|64|1<<16: the switchable variants that are off by default --
+    CTA pairs (cta_group::2) for 64-wide forward tiles and in the weight gradient, one weight-gradient CTA per SM instead of the default two;
+    7|1<<17: ONE forward / data-gradient CTA per SM for tiles <= 64 channels wide (the default co-schedules two)."""
     name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups = case
-    if tc > 1 and not (name.startswith('tc_') and (Cout % 256 == 0 or Cout == 64 or Cin == 64)):
-        pytest.skip('no optional CTA-pair variant for this geometry')
+    if tc > 1 and not (name.startswith('tc_') and (Cout % 128 == 0 or Cout <= 64 or Cin <= 64)):
+        pytest.skip('no optional variant for this geometry')
     ops.set_tensor_core_mode(tc)
     tol = 2e-5 if tc == 0 else 4e-3
     try:
