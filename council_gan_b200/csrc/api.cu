@@ -129,6 +129,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
     g_pair_mode = (mode & 8) ? 0 : (1 | ((mode & 16) ? 0 : 2) | ((mode & 32) ? 4 : 0) | ((mode & 64) ? 8 : 0));  // 64 = CTA pairs in wgrad too
     g_wgrad_xm = (mode & 128) ? 0 : 1;  // 128 = no x-on-M weight gradient for <= 64 output channels
     g_wgrad_2cta = ((mode >> 16) & 1) ? 0 : 1;  // bit 16: one weight-gradient CTA per SM (default: two co-resident CTAs)
+    g_wgrad_xm2 = ((mode >> 18) & 1) ? 0 : 1;   // bit 18: one x-on-M weight-gradient CTA per SM
     g_fwd_2cta = ((mode >> 17) & 1) ? 0 : 1;    // bit 17: one forward / dgrad CTA per SM for tiles <= 64 wide (default: two co-resident)
     g_pair_cap = (mode >> 8) & 0xff;  // bits 8..15: cap on the number of CTA pairs launched (0 = as many as are co-resident)
     return prev;

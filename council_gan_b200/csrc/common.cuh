@@ -17,6 +17,7 @@ extern int g_pair_cap;
 extern int g_wgrad_xm;
 extern int g_wgrad_2cta;
 extern int g_fwd_2cta;
+extern int g_wgrad_xm2;
 
 inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -50,6 +50,7 @@ static int g_sm_count = 0;
 int g_pair_cap = 0;
 int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
 int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
+int g_wgrad_xm2 = 1;   // ... also for the x-on-M kernel
 int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
 int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
                       // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
@@ -1524,7 +1525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad
 // block) row groups of x instead of output channels (which would leave half of every M = 128 instruction empty), dy is the N
 // operand (N = Cout).  D[(tap, ci)][co] is written back transposed: for a fixed co the 32 lanes of a warp hold 32
 // consecutive ci = one 128-byte store.  Up to Tm row tiles share the dy stage.
-__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_xm_kernel(const __grid_constant__ WgParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) wgrad_xm_kernel(const __grid_constant__ WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1544,7 +1545,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_xm_kernel(const __grid_co
     const int GPU_ = p.Tm * 4;                    // row groups per unit
     const int MG = (RG + GPU_ - 1) / GPU_;
     const int units = p.G * p.splits * MG;
-    const int tmem_cols = 2 * WG_NCOLS;
+    const int acc_cols = p.nacc == 1 ? WG_NCOLS / 2 : WG_NCOLS;  // nacc == 1 flags two co-resident CTAs: 2 x 128 columns each
+    const int tmem_cols = 2 * acc_cols;
 
     if (warp == TC_PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&p.amap);
@@ -1630,7 +1632,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_xm_kernel(const __grid_co
                 const long mend = mbeg + p.chunk < p.Mpix ? mbeg + p.chunk : p.Mpix;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WG_NCOLS);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
                 uint32_t accum = 0;
                 for (long m = mbeg; m < mend; m += p.kp) {
                     mbar_wait(&full_bar[stage], phase);
@@ -1668,7 +1670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_xm_kernel(const __grid_co
             const int ntile = (ng + 3) >> 2;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * WG_NCOLS);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
             for (int t = 0; t < ntile; t++) {
                 const int q = t * 4 + quad;          // this warp's row group inside the unit
                 const bool valid = q < ng;
@@ -1727,7 +1729,7 @@ static int wg_xm_tm(const cg_conv_geom& g) {
     return tm;
 }
 // 64-pixel stages (fewer, larger TMA boxes) for the one-CTA-per-SM kernels; the plain kernel runs two CTAs per SM with 32-pixel stages
-static bool wg_two(const cg_conv_geom& g) { return g_wgrad_2cta && !wg_pair(g) && !wg_xm(g); }
+static bool wg_two(const cg_conv_geom& g) { return g_wgrad_2cta && !wg_pair(g) && (!wg_xm(g) || g_wgrad_xm2); }
 static int wg_kp(const cg_conv_geom& g) { return (!wg_two(g) && ((long)g.B * g.Ho * g.Wo) % 64 == 0) ? 64 : 32; }
 static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
     long Mpix = (long)g.B * g.Ho * g.Wo;
@@ -1830,8 +1832,10 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     if (p.T > g.KH * g.KW) p.T = g.KH * g.KW;
     if (wg_xm(g)) {
         p.Tm = wg_xm_tm(g);
+        const bool two = wg_two(g) && p.Tm * g.Cout <= WG_NCOLS / 2;  // two co-resident CTAs: 2 x 128 TMEM columns each
+        p.nacc = two ? 1 : 2;
         int stage_bytes = p.kp * 128 * (2 + 4 * p.Tm);
-        int stages = (200 * 1024) / stage_bytes;
+        int stages = ((two ? 100 : 200) * 1024) / stage_bytes;
         if (stages > 8) stages = 8;
         p.stages = stages;
         size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
@@ -1846,7 +1850,8 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         }
         int rgs = g.KH * g.KW * (g.Cin / 32);
         long units = (long)g.G * p.splits * ((rgs + p.Tm * 4 - 1) / (p.Tm * 4));
-        int grid = (int)(units < g_sm_count ? units : g_sm_count);
+        const int slots = g_sm_count * (two ? 2 : 1);
+        int grid = (int)(units < slots ? units : slots);
         if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_xm: units=%ld splits=%d chunk=%ld stages=%d Tm=%d kp=%d\n", units, p.splits, p.chunk, stages, p.Tm, p.kp);
         wgrad_xm_kernel<<<grid, TC_THREADS, smem, st>>>(p);
         if (int rc = check_launch("wgrad_xm_kernel")) return rc;
