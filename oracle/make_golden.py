@@ -38,6 +38,9 @@ CASES = {
     'm2f64_n4_b2': ('male2female', {}, 64, 2, 60001),
     # selfie2anime: b2a-only direction (gan_w asymmetry trainer_council.py:775-777), focus weights 0
     'anime64_n3_b2': ('selfie2anime', {'council.council_size': 3}, 64, 2, 2001),
+    # BASELINE.json configs[1] at its real resolution (256x256: every layer geometry of the headline workload), council and batch
+    # reduced so that the CPU reference and the oracle finish in seconds
+    'm2f256_n2_b1': ('male2female', {'council.council_size': 2}, 256, 1, 60001),
 }
 
 PROBE_PARAMS = {

@@ -7,7 +7,7 @@ import council_oracle as co
 from common import close, load_golden, probe, run_oracle_iteration
 from make_golden import PROBE_PARAMS
 
-CASES = ['glasses64_n2_b2_early', 'm2f64_n4_b2', 'anime64_n3_b2', 'glasses128_n2_b1']
+CASES = ['glasses64_n2_b2_early', 'm2f64_n4_b2', 'anime64_n3_b2', 'glasses128_n2_b1', 'm2f256_n2_b1']
 RTOL = 2e-5  # both sides are torch-CPU fp32; the slack covers thread-count dependent summation order
 
 
