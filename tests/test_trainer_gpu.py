@@ -32,6 +32,10 @@ def run_cuda(gold, tc):
 @pytest.mark.parametrize('case', ['glasses64_n2_b2_early', 'anime64_n3_b2', 'm2f64_n4_b2', 'glasses128_n2_b1'])
 @pytest.mark.parametrize('tc', [0, 1])
 def test_iteration_matches_oracle_and_golden(case, tc):
+    check_iteration(case, tc)
+
+
+def check_iteration(case, tc):
     gold = load_golden(case)
     torch.set_num_threads(max(1, torch.get_num_threads()))
     orc, hp = run_oracle(gold, torch.float32)
@@ -89,3 +93,12 @@ def test_member_api_encode_decode():
         for k in p:
             assert torch.equal(sd[k].cpu(), p[k]), k
     tr.ops.set_tensor_core_mode(1)
+
+
+# Kept LAST among the GPU tests: the 256x256 fixture (BASELINE configs[1] geometry, council 2, batch 1) was generated after this
+# round's GPU budget was spent.  It runs and its outcome is reported (xfail / xpass) without gating the suite; it becomes a hard
+# case of test_iteration_matches_oracle_and_golden once it has been seen green on a B200.
+@pytest.mark.xfail(strict=False, reason='not yet run on a GPU (fixture added at the end of round 1)')
+@pytest.mark.parametrize('tc', [0, 1])
+def test_full_resolution_iteration(tc):
+    check_iteration('m2f256_n2_b1', tc)
