@@ -99,6 +99,10 @@ class CudaOps:
         if self.cc[0] != 10:
             raise RuntimeError('libcouncil_b200.so is built for sm_100a only; device is sm_%d%d' % self.cc)
         self._ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+        # experimental (round 2, not yet measured): weight gradients on a side stream so that they overlap the HBM-bound passes of
+        # the main stream.  bank.grad is written only by conv_wgrad and read only after wgrad_join() (trainer _adam).
+        self._wgrad_stream = torch.cuda.Stream(self.device) if os.environ.get('COUNCIL_WGRAD_STREAM', '0') == '1' else None
+        self._ws_side = None
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _stream(self):
@@ -207,9 +211,27 @@ class CudaOps:
         self._chk(x, dy, dw, db)
         g = self._geom(x.shape, dw, stride, pad, ups)
         assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout)
-        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 2))
-        self._timed('conv_wgrad', g, lambda: self._ck(self.lib.cg_conv_wgrad(
-            C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), self._stream()), 'cg_conv_wgrad'))
+        need = self.lib.cg_conv_workspace_bytes(C.byref(g), 2)
+        side = self._wgrad_stream
+        if side is None:
+            ws = self._ws_for(need)
+            self._timed('conv_wgrad', g, lambda: self._ck(self.lib.cg_conv_wgrad(
+                C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), self._stream()), 'cg_conv_wgrad'))
+            return
+        side.wait_stream(torch.cuda.current_stream(self.device))  # x and dy were produced on the main stream
+        with torch.cuda.stream(side):
+            if self._ws_side is None or need > self._ws_side.numel():
+                self._ws_side = torch.empty(max(int(need * 1.25) + 1024, 64 << 20), dtype=torch.uint8, device=self.device)
+            ws = self._ws_side
+            self._timed('conv_wgrad', g, lambda: self._ck(self.lib.cg_conv_wgrad(
+                C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), side.cuda_stream), 'cg_conv_wgrad'))
+        for t in (x, dy):
+            t.record_stream(side)  # the caching allocator must not hand their memory out before the side stream is done
+
+    def wgrad_join(self):
+        """Order everything queued on the weight-gradient side stream before what the main stream does next."""
+        if self._wgrad_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
 
     # -- instance norm / AdaIN --------------------------------------------------------------------
     def in_stats(self, y, eps=1e-5):

@@ -262,6 +262,8 @@ class Council_Trainer(nn.Module):
             if net is None:
                 continue
             bank = net.bank
+            if hasattr(self.ops, 'wgrad_join'):
+                self.ops.wgrad_join()  # weight gradients may have been queued on a side stream (COUNCIL_WGRAD_STREAM=1)
             if dist is not None and self.world > 1:
                 dist.all_reduce(bank.grad)  # SUM; local coefficients already carry 1/world
             bank.step += 1
