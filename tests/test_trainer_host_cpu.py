@@ -129,7 +129,7 @@ def test_host_logic_exact_in_fp64(case):
     print(case, 'fp64 worst grad relL2 %.2e, worst post-step parameter diff %.2e' % (wg, wp))
 
 
-@pytest.mark.parametrize('case', ['glasses64_n2_b2_early', 'm2f64_n4_b2'])
+@pytest.mark.parametrize('case', ['glasses64_n2_b2_early', 'm2f64_n4_b2', 'm2f256_n2_b1'])
 def test_host_logic_fp32_vs_oracle_and_golden(case):
     gold = load_golden(case)
     torch.set_num_threads(8)
