@@ -11,8 +11,16 @@ Default workload = BASELINE.json configs[1]: male2female 256x256, council_size=4
 Prints ONE JSON line (rank 0).  `value` = images/sec with inputs resident in HBM; `e2e` = the same through
 the public Council_Trainer API with HOST (pinned) image tensors: H2D copies and the D2H loss read are inside
 the timed region.  `roofline` is for the dominant convolution kernel, timed live with CUDA events on the
-launching stream.  `cpu_baseline` / `--impl reference` time the CPU oracle port (oracle/council_oracle.py, a
-restatement of the reference validated against it) on the host cores on a bounded sample (batch 1).
+launching stream.
+
+Comparison legs (measurement infrastructure, baseline/ref_runner.py):
+  * `cpu_baseline` / `--impl reference`: the UNMODIFIED reference (`$COUNCIL_REF_DIR` -> /root/reference -> baseline/_ref; else the
+    oracle port, `kind: "port"`) on the host cores, on a bounded sample of the workload (batch 1 -- the batch really run is
+    printed), with the thread count chosen by a sweep at THIS workload (host core count printed);
+  * `gpu_library_baseline` (and `--impl reference-gpu`): the same unmodified reference on the same B200 under stock
+    PyTorch + cuDNN at the workload's full batch (train.py:241-251 path, cudnn.deterministic as train.py:61, plus a
+    cudnn.benchmark number) -- the comparator SURVEY.md 2.1 names.
+Before timing, the first step of our arm is checked against the reference's golden losses for the workload (1e-3).
 """
 from __future__ import annotations
 
@@ -96,31 +104,101 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def cpu_oracle_rate(workload, steps, warmup):
-    """images/sec of the CPU oracle port on a bounded sample (batch 1) of the workload."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import council_oracle as co
+GOLDEN_FOR = {'male2female_256_n4_b8': 'm2f256_n4_b8', 'selfie2anime_256_n4_b4': 'anime256_n4_b4',
+              'male2female_512_n6_b2': 'm2f512_n6_b2', 'glasses_128_n2_b1': 'glasses128_n2_b1'}
+
+
+def reference_cpu_rate(workload, steps, warmup):
+    """images/sec of the reference's own CPU implementation on a bounded sample (batch 1) of the workload.
+    -> (rate, seconds per step, info dict for cpu_baseline)."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_runner as rr
     hp, n, b, size, it = load_hp(workload)
-    hp['batch_size'] = 1
-    cores = min(os.cpu_count() or 1, int(os.environ.get('COUNCIL_CPU_THREADS', '8')))  # measured on the 128-core box: 8 threads 2.07 s, 32 threads 2.78 s, 128 threads > 200 s (glasses 128x128)
+    sample_batch = 1
+    hp['batch_size'] = sample_batch
+    host = os.cpu_count() or 1
+    x_a, x_b = synth(sample_batch, size, 123)
+    ref_dir = rr.find_reference()
+    if ref_dir is not None:
+        tr, _ = rr.build_reference_trainer(hp, 'cpu', ref_dir)
+        kind, what = 'reference', 'the unmodified reference (%s) on CPU, .cuda(dev) rebound to .to(dev)' % ref_dir
+    else:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import council_oracle as co
+        tr = co.OracleTrainer(hp, co.synth_all_states(hp, seed=7))
+        co.seed_all(1)
+        kind, what = 'port', 'oracle/council_oracle.py (plain-PyTorch restatement pinned against the reference; no reference tree on this box)'
+    step = rr.make_step(tr, hp, x_a, x_b, it)
+    # thread count: measured at THIS workload (one dis_update per candidate), not assumed
+    forced = os.environ.get('COUNCIL_CPU_THREADS')
+    sweep = {}
+    if forced:
+        cores = max(1, min(host, int(forced)))
+    else:
+        cands = sorted(set(c for c in (4, 8, 16, 32, 64, host) if c <= host))
+        torch.set_num_threads(cands[0])
+        hp['iteration'] = it
+        tr.dis_update(x_a, x_b, hp)  # page-in / allocator warm-up
+        for c in cands:
+            torch.set_num_threads(c)
+            t0 = time.perf_counter()
+            tr.dis_update(x_a, x_b, hp)
+            sweep[str(c)] = round(time.perf_counter() - t0, 3)
+            if sweep[str(c)] > 3.0 * min(sweep.values()):
+                break  # oversubscribed: larger counts only get worse
+        cores = int(min(sweep, key=sweep.get))
     torch.set_num_threads(cores)
-    states = co.synth_all_states(hp, seed=7)
-    tr = co.OracleTrainer(hp, states)
-    co.seed_all(1)
-    x_a, x_b = synth(1, size, 123)
+    dt = rr.time_cpu(step, steps, warmup)
+    info = {'value': sample_batch / dt, 'unit': 'images/s', 'cores': cores, 'host_cores': host, 'kind': kind,
+            'unmodified': kind == 'reference', 'batch_ran': sample_batch, 'thread_sweep_s_per_dis_update': sweep,
+            'sample': 'one full iteration (dis + dis_council + gen update) of the same config at batch %d (config batch %d): %s; '
+                      '%d torch threads chosen by the sweep on a %d-core host' % (sample_batch, b, what, cores, host)}
+    return sample_batch / dt, dt, info
 
-    def step():
-        tr.dis_update(x_a, x_b, hp)
-        tr.dis_council_update(x_a, x_b, hp)
-        tr.gen_update(x_a, x_b, hp, it)
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return 1.0 / dt, dt, cores
+def reference_cpu_subprocess(workload):
+    """cpu_baseline leg of our arm: the reference arm in a clean process (its .cuda shim and thread settings stay there)."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', workload, '--steps', '1',
+                        '--warmup', '1'], capture_output=True, text=True, timeout=1500, cwd=ROOT,
+                       env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')})
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith('{'):
+            return json.loads(line)['cpu_baseline']
+    return {'error': (r.stderr or r.stdout)[-400:]}
+
+
+def parity_check(trainer_cls, workload, dev, tc):
+    """First step of our arm vs the reference's golden losses for this workload (tests/golden, generated from the unmodified
+    reference by oracle/make_golden.py).  Checker use of oracle/ only: the synthetic parameter/input generators."""
+    case = GOLDEN_FOR.get(workload)
+    path = os.path.join(ROOT, 'tests', 'golden', '%s.json' % case)
+    if case is None or not os.path.exists(path):
+        return {'checked': False, 'why': 'no golden fixture for this workload'}
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import council_oracle as co
+    from common import load_golden, setup_case
+    gold = load_golden(case)
+    hp, states, x_a, x_b = setup_case(gold)
+    co.seed_all(hp['random_seed'])
+    tr = trainer_cls(hp, dev)
+    tr.ops.set_tensor_core_mode(tc)
+    for name, lst in states.items():
+        fam, d = name.rsplit('_', 1)
+        for i, sd in enumerate(lst):
+            getattr(tr, '%s_%s_s' % (fam, d))[i].load_state_dict(sd)
+    co.seed_all(gold['rng_seed'])
+    tr.dis_update(x_a, x_b, hp)
+    tr.dis_council_update(x_a, x_b, hp)
+    tr.gen_update(x_a, x_b, hp, gold['iteration'])
+    worst = 0.0
+    for got, want in ((tr.loss_dis_total_s, gold['loss_dis_total']), (tr.loss_dis_council_total_s, gold['loss_dis_council_total']),
+                      (tr.loss_gen_total_s, gold['loss_gen_total'])):
+        for g, w in zip(got, want):
+            worst = max(worst, abs(float(g) - w) / abs(w))
+    del tr
+    torch.cuda.empty_cache()
+    return {'checked': True, 'case': case, 'worst_rel_loss_err_vs_reference': worst, 'tol': 1e-3, 'ok': bool(worst < 1e-3)}
 
 
 def main():
@@ -128,9 +206,11 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='male2female_256_n4_b8', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-baseline', action='store_true')
+    ap.add_argument('--no-parity-check', action='store_true')
     ap.add_argument('--tc', type=int, default=1, help='0: SIMT fp32 kernels only, 1: tcgen05 TF32 where supported')
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -144,18 +224,36 @@ def main():
               'image': '%dx%d' % (size, size), 'parallelism': 'dp%d' % world, 'iteration': it,
               'l2': 'per-step working set (saved activations, several GB) >> 126 MB L2; no explicit flush'}
 
-    # ------------------------------------------------------------------ reference arm: CPU oracle port
+    # ------------------------------------------------------------------ reference arm: the reference's own CPU path
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        rate, dt, cores = cpu_oracle_rate(args.workload, args.steps, args.warmup)
+        rate, dt, info = reference_cpu_rate(args.workload, args.steps, args.warmup)
+        config['batch_ran'] = info['batch_ran']
         line = {'impl': 'reference', 'metric': metric, 'value': rate, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': rate, 'unit': unit, 'cores': cores, 'kind': 'port',
-                                 'sample': 'one full iteration (dis+dis_council+gen) at batch 1 of the same config; '
-                                           'oracle/council_oracle.py (torch CPU fp32), validated against the reference'},
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'cpu_baseline': info,
                 'e2e': {'value': rate, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ library-kernel arm: the reference on the GPU (stock PyTorch + cuDNN)
+    if args.impl == 'reference-gpu':
+        if rank != 0:
+            return 0
+        sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+        import ref_runner as rr
+        torch.cuda.set_device(local_rank)
+        dev = 'cuda:%d' % local_rank
+        x_a, x_b = synth(batch, size, 123)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        info = rr.gpu_library_baseline(hp, x_a, x_b, it, dev, steps=args.steps, warmup=args.warmup)
+        clocks = sampler.stop()
+        line = {'impl': 'reference-gpu', 'metric': metric, 'value': info['value'], 'unit': unit, 'n_gpus': 1, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'tf32 (cudnn.allow_tf32 as shipped)', 'data': 'synthetic', 'config': config,
+                'clocks': clocks, 'gpu_library_baseline': info}
         print(json.dumps(line))
         return 0
 
@@ -169,6 +267,14 @@ def main():
     from council_gan_b200 import Council_Trainer
     import random
     import numpy as np
+    random.seed(1)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    parity = None
+    if world == 1 and not args.no_parity_check:
+        parity = parity_check(Council_Trainer, args.workload, dev, args.tc)
+        if parity.get('checked') and not parity['ok']:
+            print('PARITY CHECK FAILED: %r' % (parity,), file=sys.stderr)
     random.seed(1)
     np.random.seed(1)
     torch.manual_seed(1)
@@ -218,19 +324,28 @@ def main():
     ms_per_step = ms / args.steps
     value = batch * world / (ms_per_step * 1e-3)
 
-    # end to end through the public API with host tensors (H2D inside, loss read back)
+    # end to end through the public API with HOST tensors: every step gets its own pinned minibatch (as train.py:225-228's data
+    # loader does), so the H2D copy and the NCHW -> channels-last conversion happen inside every timed step; the losses are
+    # read back to the host at the end of every step
     d2h = [0]
+    host_batches = [(xa_h.clone().pin_memory(), xb_h.clone().pin_memory()) for _ in range(args.steps + 1)]
+    it_host = iter(host_batches)
+    misses0 = trainer.img_cache_misses
 
     def e2e_step():
-        step(xa_h, xb_h)
+        xa, xb = next(it_host)
+        step(xa, xb)
         vals = [float(v) for v in trainer.loss_gen_total_s] + [float(v) for v in trainer.loss_dis_total_s]
         d2h[0] = 4 * len(vals) + 4 * 6 * n_members
         return vals
 
     e2e_step()
+    m1 = trainer.img_cache_misses
     ms_e2e = timed(e2e_step, args.steps) / args.steps
+    assert trainer.img_cache_misses - m1 == 2 * args.steps, 'every e2e step must upload its own two image batches'
     e2e = {'value': batch * world / (ms_e2e * 1e-3), 'unit': unit, 'ms_per_step': ms_e2e,
-           'h2d_bytes_per_step': int(2 * xa_h.numel() * 4), 'd2h_bytes_per_step': int(d2h[0])}
+           'h2d_bytes_per_step': int(2 * xa_h.numel() * 4), 'd2h_bytes_per_step': int(d2h[0]),
+           'fresh_host_tensors_per_step': True, 'image_uploads_in_timed_region': int(trainer.img_cache_misses - m1)}
 
     if rank != 0:
         if world > 1:
@@ -260,14 +375,15 @@ def main():
         key, (tot_ms, cnt, flops) = max(ktimes.items(), key=lambda kv: kv[1][0])
         tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2.0  # TF32 runs at half the bf16 tensor rate
         ach = flops / (tot_ms / cnt * 1e-3) / 1e12
-        traffic = None
+        traffic = tensor_pipe = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(key, {}).get('traffic_bytes')
+            ent = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(key, {})
+            traffic, tensor_pipe = ent.get('traffic_bytes'), ent.get('tensor_pipe_pct')
         except Exception:
             pass
         roofline = {'bound': 'tensor', 'kernel': key, 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
                     'frac_of_nominal_tf32_1100': ach / 1100.0, 'flops_per_launch': flops,
-                    'traffic': traffic, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
+                    'traffic': traffic, 'tensor_pipe_pct_ncu': tensor_pipe, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
                     'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 operands)' if peaks else 'fallback 1400/2')}
     alg_tflop = 2 * ALG_GMAC_PER_IMAGE_MEMBER_256 * 1e9 * scale * n_members * batch * world / 1e12
     line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -280,11 +396,21 @@ def main():
             'hbm_kernel_times_ms_per_step': ({k[4:]: round(v[0] / args.steps, 3) for k, v in sorted(hbm_times.items(), key=lambda kv: -kv[1][0])[:20]}
                                              if hbm_times else None),
             'losses': {'gen': [float(v) for v in trainer.loss_gen_total_s], 'dis': [float(v) for v in trainer.loss_dis_total_s]}}
+    line['parity_check'] = parity
+    if world == 1 and not args.no_gpu_baseline:
+        # the comparator SURVEY.md 2.1 / 8d names: the unmodified reference on this same GPU under stock PyTorch + cuDNN
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+        import ref_runner as rr
+        try:
+            gb = rr.gpu_library_baseline(hp, xa_h, xb_h, it, dev, steps=10, warmup=3)
+            gb['ours_over_baseline'] = value / gb['value']
+            gb['ours_over_baseline_cudnn_benchmark'] = value / gb['value_cudnn_benchmark'] if gb.get('value_cudnn_benchmark') else None
+        except Exception as e:  # the comparison leg must never take the product line down
+            gb = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+        line['gpu_library_baseline'] = gb
     if not args.no_cpu_baseline:
-        rate, dt, cores = cpu_oracle_rate(args.workload, 1, 1)
-        line['cpu_baseline'] = {'value': rate, 'unit': unit, 'cores': cores, 'kind': 'port',
-                                'sample': 'one full iteration at batch 1 of the same config after one warm-up '
-                                          '(oracle/council_oracle.py, torch CPU fp32, %d threads)' % cores}
+        line['cpu_baseline'] = reference_cpu_subprocess(args.workload)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -167,15 +167,16 @@ __global__ void acc_slice_kernel(float* __restrict__ dst, const float* __restric
     for (int c = 0; c < nch; c++) dst[i * Cd + c] += __ldg(src + i * Cs + c);
 }
 
-__global__ void gather_images_kernel(const float* __restrict__ pool, const int32_t* __restrict__ idx,
-                                     const float* __restrict__ x_in, float* __restrict__ y, long total, int Bt, int B, int HW) {
+__global__ void gather_images_kernel(const float* __restrict__ pool0, int n0, const float* __restrict__ pool1,
+                                     const int32_t* __restrict__ idx, const float* __restrict__ x_in, float* __restrict__ y,
+                                     long total, int Bt, int B, int HW) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int pix = (int)(i % HW);
     long gn = i / HW;  // g*Bt + n
     int n = (int)(gn % Bt);
     int slot = __ldg(idx + gn);
-    float4 v = f4(pool + ((long)slot * HW + pix) * 4);
+    float4 v = slot < n0 ? f4(pool0 + ((long)slot * HW + pix) * 4) : f4(pool1 + ((long)(slot - n0) * HW + pix) * 4);
     if (x_in) {
         float4 u = f4(x_in + ((long)(n % B) * HW + pix) * 4);
         reinterpret_cast<float4*>(y)[i * 2] = v;
@@ -349,10 +350,10 @@ extern "C" int cg_acc_slice(float* dst, const float* src, long npix, int Cd, int
     acc_slice_kernel<<<cdiv(npix, 256), 256, 0, ST>>>(dst, src, npix, Cd, Cs, nch);
     return check_launch("acc_slice");
 }
-extern "C" int cg_gather_images(const float* pool, const int32_t* idx, const float* x_in, float* y, int G, int Bt, int B, int HW,
-                                void* stream) {
+extern "C" int cg_gather_images(const float* pool0, int n0, const float* pool1, const int32_t* idx, const float* x_in, float* y,
+                                int G, int Bt, int B, int HW, void* stream) {
     long total = (long)G * Bt * HW;
-    gather_images_kernel<<<cdiv(total, 256), 256, 0, ST>>>(pool, idx, x_in, y, total, Bt, B, HW);
+    gather_images_kernel<<<cdiv(total, 256), 256, 0, ST>>>(pool0, n0, pool1, idx, x_in, y, total, Bt, B, HW);
     return check_launch("gather_images");
 }
 extern "C" int cg_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, void* stream) {

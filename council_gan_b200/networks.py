@@ -90,15 +90,17 @@ class LayerSpec:
         return (w.reshape(self.cout, self.cin) if self.linear else w).contiguous().clone()
 
     def import_weight(self, dst, ref):  # dst: [Cout,KH,KW,Cin_p] view; ref: reference tensor
-        ref = ref.to(dst.device, dst.dtype)
+        """OIHW -> the kernel layout, assembled on the HOST and moved with one plain copy (no permute / fill kernels on the
+        device: checkpoint loading stays out of the kernel launch list)."""
+        ref = ref.detach().to('cpu', dst.dtype)
         if self.linear:
             ref = ref.reshape(self.cout, self.cin, 1, 1)
         ref = ref.permute(0, 2, 3, 1)
         if self.lanes is not None:
-            dst.zero_()
-            dst[..., self.lanes] = ref
-        else:
-            dst.copy_(ref)
+            full = torch.zeros(dst.shape, dtype=dst.dtype)
+            full[..., self.lanes] = ref
+            ref = full
+        dst.copy_(ref.contiguous())
 
 
 class MemberView:
@@ -151,7 +153,14 @@ class _StackedNet:
     def extra_state(self):
         return OrderedDict()
 
+    _before_access = None  # set by the trainer: joins a pending (data-parallel, deferred) optimiser step of this family
+
+    def _sync(self):
+        if self._before_access is not None:
+            self._before_access()
+
     def member_state_dict(self, i):
+        self._sync()
         sd = OrderedDict()
         for spec in self._specs():
             b = self._bank_of(spec.wname)
@@ -164,6 +173,7 @@ class _StackedNet:
         return OrderedDict((k, sd[k]) for k in order)
 
     def load_member_state_dict(self, i, sd, strict=True):
+        self._sync()
         keys = set(self.reference_key_order())
         if strict:
             missing, unexpected = keys - set(sd), set(sd) - keys
@@ -174,7 +184,7 @@ class _StackedNet:
             if spec.wname in sd:
                 spec.import_weight(b.p(spec.wname)[i], sd[spec.wname])
             if spec.bname in sd:
-                b.p(spec.bname)[i].copy_(sd[spec.bname].to(b.data.device, b.data.dtype).reshape(-1))
+                b.p(spec.bname)[i].copy_(sd[spec.bname].detach().to('cpu', b.data.dtype).reshape(-1))
         self.params_changed()
 
     def params_changed(self):
@@ -277,6 +287,9 @@ class CouncilGen(_StackedNet):
             [s for ab in self.dec_up for s in ab] + self.head + self.mlp
         self.live_specs = live
         self.bank = ParamBank(ops, G, [e for s in live for e in s.entries()])
+        # flat-buffer offset where the content encoder's parameters end: the decoder / head / MLP gradients [enc_end:] are
+        # complete before the encoder backward starts, so data parallelism all-reduces them while it runs
+        self.enc_end = self.bank.table[self.dec_res[0][0].wname][0] if self.dec_res else self.bank.table[self.head[0].wname][0]
         self.frozen = ParamBank(ops, G, [e for s in self.sty + [self.sty_out] for e in s.entries()], trainable=False)
         # biases feeding IN / AdaIN are mathematically dead: their gradient is exactly 0 here
         self.dead_bias = set(s.bname for s in live if s not in self.head and s not in self.mlp)
@@ -407,13 +420,14 @@ class CouncilGen(_StackedNet):
         return x_fake, mask
 
     # -- backward (gen_update only) -------------------------------------------------------------------
-    def backward(self, d_xfake, d_mask, enc_saved, dec_saved):
-        """Fills ``self.bank.grad`` for every live parameter given d(loss)/d(x_fake), d(loss)/d(mask)."""
+    def backward(self, d_xfake, d_mask, enc_saved, dec_saved, on_decoder_done=None):
+        """Fills ``self.bank.grad`` for every live parameter given d(loss)/d(x_fake), d(loss)/d(mask).
+        on_decoder_done: called when grad[enc_end:] (decoder, head, MLP) is final, before the encoder backward."""
         ops, bank = self.ops, self.bank
         dec_saved = list(dec_saved)
         adain, acts, x_img = dec_saved.pop()
         mlp_acts = dec_saved.pop(0)
-        d_adain = ops.zeros(*adain.shape)
+        d_adain = ops.empty(*adain.shape)  # every column is written by exactly one AdaIN layer's backward
         # head: 1x1 convs with fused activations
         d = ops.mask_head_bwd(acts[3], x_img, d_xfake, d_mask)  # grad w.r.t. pre-tanh output of head[2]
         for li in (2, 1, 0):
@@ -446,6 +460,8 @@ class CouncilGen(_StackedNet):
             ops.conv_wgrad(h_in, dm, bank.g(s.wname), bank.g(s.bname), 1, 0)
             if li > 0:
                 dm = ops.conv_dgrad(dm, bank.p(s.wname), h_in.shape, 1, 0, mask_src=h_in, mask_slope=0.0)
+        if on_decoder_done is not None:
+            on_decoder_done()
         # content encoder
         recs = list(enc_saved)
         k = len(recs) - 1
@@ -461,25 +477,34 @@ class CouncilGen(_StackedNet):
 
     # -- single-member API (reference's gen.encode / gen.decode on NCHW tensors) -----------------------
     def member_encode(self, i, images):
+        self._sync()
         ops = self.ops
         x = ops.nchw_to_nhwc(images.to(ops.device, ops.dtype).contiguous(), IMG_C)[None]
         c = self.encode(x, None, sl=i)
         content = ops.nhwc_to_nchw(c[0], self.cdim)
         return content, self.member_style_encode(i, x)
 
-    def member_style_encode(self, i, x):
-        """StyleEncoder networks.py:337-353 (norm none, relu) -> [B, style_dim, 1, 1]."""
+    def style_encode(self, x, sl=None):
+        """StyleEncoder networks.py:337-353 (norm none, relu), all members (or member sl) at once:
+        x [1,B,H,W,4] -> style codes [G,B,1,1,style_dim].  Not on the training path (its result is discarded there)."""
         ops, fz = self.ops, self.frozen
+
+        def wb(s):
+            w, b = fz.p(s.wname), fz.p(s.bname)
+            return (w, b) if sl is None else (w[sl:sl + 1], b[sl:sl + 1])
         h = x
         for s in self.sty:
-            h = ops.conv_fwd(h, fz.p(s.wname)[i:i + 1], fz.p(s.bname)[i:i + 1], s.stride, s.pad, act=ACT_RELU)
-        # global average pool (tiny, host-side plumbing) then the 1x1 conv as a linear layer
+            h = ops.conv_fwd(h, *wb(s), s.stride, s.pad, act=ACT_RELU)
+        # global average pool (tiny, plumbing) then the 1x1 conv as a linear layer
         pooled = h.mean(dim=(2, 3), keepdim=True).contiguous()
-        s = self.sty_out
-        out = ops.conv_fwd(pooled, fz.p(s.wname)[i:i + 1], fz.p(s.bname)[i:i + 1], 1, 0)
-        return out[0].permute(0, 3, 1, 2).contiguous()
+        return ops.conv_fwd(pooled, *wb(self.sty_out), 1, 0)
+
+    def member_style_encode(self, i, x):
+        """-> [B, style_dim, 1, 1] of member i (AdaINGen.encode's second result, networks.py:278-283)."""
+        return self.style_encode(x, sl=i)[0].permute(0, 3, 1, 2).contiguous()
 
     def member_decode(self, i, content, style, images):
+        self._sync()
         ops = self.ops
         x = ops.nchw_to_nhwc(images.to(ops.device, ops.dtype).contiguous(), IMG_C)[None]
         c = ops.nchw_to_nhwc(content.to(ops.device, ops.dtype).contiguous(), self.cdim)[None]

@@ -25,6 +25,29 @@ class ConvGeom(C.Structure):
                                          'KH', 'KW', 'stride', 'pad', 'ups')]
 
 
+LOSS_MAX_MAPS, LOSS_MAX_G, LOSS_MAX_SEG = 4, 8, 8
+
+
+class LsganDesc(C.Structure):  # cg_lsgan_desc
+    _fields_ = [('nmaps', C.c_int32), ('G', C.c_int32), ('nseg', C.c_int32), ('_pad', C.c_int32),
+                ('out', C.c_void_p * LOSS_MAX_MAPS), ('dout', C.c_void_p * LOSS_MAX_MAPS),
+                ('n_per_seg', C.c_int32 * LOSS_MAX_MAPS), ('target', C.c_float * LOSS_MAX_SEG),
+                ('weight', (C.c_float * LOSS_MAX_SEG) * LOSS_MAX_G), ('loss_scale', C.c_float), ('grad_scale', C.c_float)]
+
+
+class GenLossDesc(C.Structure):  # cg_gen_loss_desc
+    _fields_ = [('G', C.c_int32), ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('n_adv', C.c_int32), ('n_cl', C.c_int32),
+                ('adv_out', C.c_void_p * 2), ('adv_dout', C.c_void_p * 2), ('cl_out', C.c_void_p * 2), ('cl_dout', C.c_void_p * 2),
+                ('adv_n', C.c_int32 * 2), ('cl_n', C.c_int32 * 2), ('mask', C.c_void_p),
+                ('center', C.c_float), ('eps', C.c_float), ('adv_grad_scale', C.c_float), ('_pad', C.c_float)]
+
+
+class GenLossHp(C.Structure):  # cg_gen_loss_hp
+    _fields_ = [(n, C.c_int32) for n in ('world', 'hist_size', 'head_gan', 'head_council', 'gan_on', 'council_on', 'focus_on',
+                                         'matching', 'small_abs', 'small_square')] + \
+               [(n, C.c_double) for n in ('gan_w', 'council_w', 'w01', 'wtot', 'wtv', 'numel')]
+
+
 _fp = C.c_void_p
 _SIGS = {
     'cg_last_error': (C.c_char_p, []),
@@ -46,13 +69,17 @@ _SIGS = {
     'cg_avgpool_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_avgpool_bwd': (C.c_int, [_fp, _fp] + [C.c_int] * 7 + [_fp]),
     'cg_acc_slice': (C.c_int, [_fp, _fp, C.c_long, C.c_int, C.c_int, C.c_int, _fp]),
-    'cg_gather_images': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_gather_images': (C.c_int, [_fp, C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_nchw_to_nhwc': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_nhwc_to_nchw': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_lsgan_fwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_lsgan_bwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_focus_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_focus_bwd': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
+    'cg_lsgan_fused': (C.c_int, [C.POINTER(LsganDesc), _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
+    'cg_gen_loss_fwd': (C.c_int, [C.POINTER(GenLossDesc), _fp, _fp, C.c_size_t, _fp]),
+    'cg_gen_loss_bwd': (C.c_int, [C.POINTER(GenLossDesc), C.POINTER(GenLossHp), _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    'cg_loss_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'cg_adam_step': (C.c_int, [_fp, _fp, _fp, _fp, C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, _fp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -99,6 +126,12 @@ class CudaOps:
         if self.cc[0] != 10:
             raise RuntimeError('libcouncil_b200.so is built for sm_100a only; device is sm_%d%d' % self.cc)
         self._ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+        # dedicated, zero-initialised scratch of the fused loss kernels (ticket counter + partial sums); grown on demand
+        self._loss_ws = torch.zeros(1 << 16, dtype=torch.uint8, device=self.device)
+        # small per-step host data (style noise, peer index tables): ONE pinned staging buffer and ONE async H2D copy per
+        # update instead of a pageable `torch.tensor(...).to(device)` (a hidden host sync) per table
+        self._stage_ring = [None] * 8
+        self._stage_next = 0
         # experimental (round 2, not yet measured): weight gradients on a side stream so that they overlap the HBM-bound passes of
         # the main stream.  bank.grad is written only by conv_wgrad and read only after wgrad_join() (trainer _adam).
         self._wgrad_stream = torch.cuda.Stream(self.device) if os.environ.get('COUNCIL_WGRAD_STREAM', '0') == '1' else None
@@ -315,16 +348,48 @@ class CudaOps:
         self._ck(self.lib.cg_acc_slice(_p(dst), _p(src), npix, dst.shape[-1], src.shape[-1], nch, self._stream()),
                  'cg_acc_slice')
 
-    def gather_images(self, pool, idx, x_in, G, Bt):
-        """pool [S,H,W,4]; idx int32 [G,Bt] slot table; x_in [1,B,H,W,4] or None -> [G,Bt,H,W,4|8]"""
-        self._chk(pool, x_in)
+    def gather_images(self, pools, idx, x_in, G, Bt):
+        """pools: one or two tensors [S_k,H,W,4] (slot k < S_0 reads pools[0], else pools[1] -- no torch.cat); idx int32
+        [G,Bt] slot table on the device; x_in [1,B,H,W,4] or None -> [G,Bt,H,W,4|8]"""
+        if torch.is_tensor(pools):
+            pools = (pools,)
+        self._chk(x_in, *pools)
         assert idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.numel() == G * Bt
-        S, H, W, _ = pool.shape
+        S0, H, W, _ = pools[0].shape
+        p1 = pools[1] if len(pools) > 1 else None
         B = x_in.shape[1] if x_in is not None else 1
         y = self.empty(G, Bt, H, W, 8 if x_in is not None else 4)
-        self._ck(self.lib.cg_gather_images(_p(pool), idx.data_ptr(), _p(x_in), _p(y), G, Bt, B, H * W, self._stream()),
-                 'cg_gather_images')
+        self._ck(self.lib.cg_gather_images(_p(pools[0]), S0, _p(p1), idx.data_ptr(), _p(x_in), _p(y), G, Bt, B, H * W,
+                                           self._stream()), 'cg_gather_images')
         return y
+
+    # -- host -> device staging -------------------------------------------------------------------
+    def stage(self, arrays):
+        """arrays: list of CPU tensors (float32 / int32).  Packs them into one pinned buffer, issues ONE asynchronous H2D
+        copy on the current stream and returns device views with the same shapes / dtypes."""
+        sizes = [(a.numel() * 4 + 15) // 16 * 16 for a in arrays]
+        total = max(16, sum(sizes))
+        k = self._stage_next
+        self._stage_next = (k + 1) % len(self._stage_ring)
+        slot = self._stage_ring[k]
+        if slot is None or slot[0].numel() < total:
+            cap = max(total, 1 << 16)
+            slot = [torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(cap, dtype=torch.uint8, device=self.device), None]
+            self._stage_ring[k] = slot
+        host, dev, ev = slot
+        if ev is not None:
+            ev.synchronize()  # the copy that last used this pinned buffer (8 updates ago) has long finished
+        off, views = 0, []
+        for a, sz in zip(arrays, sizes):
+            assert a.dtype in (torch.float32, torch.int32) and not a.is_cuda
+            n = a.numel() * 4
+            host[off:off + n].view(a.dtype).copy_(a.reshape(-1))
+            views.append(dev[off:off + n].view(a.dtype).view(a.shape))
+            off += sz
+        dev[:off].copy_(host[:off], non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record()
+        return views
 
     def nchw_to_nhwc(self, x, Cp):
         self._chk(x)
@@ -381,6 +446,82 @@ class CudaOps:
         self._ck(self.lib.cg_focus_bwd(_p(mask), _p(coef), _p(dmask), G, B, H, W, center, eps, self._stream()),
                  'cg_focus_bwd')
         return dmask
+
+    # -- fused losses (the training path uses these; the four calls above remain for the per-kernel tests) --------
+    def _loss_scratch(self, G, B=0, H=0, W=0):
+        need = int(self.lib.cg_loss_workspace_bytes(G, B, H, W))
+        if need > self._loss_ws.numel():
+            self._loss_ws = torch.zeros(need + 4096, dtype=torch.uint8, device=self.device)
+        return self._loss_ws
+
+    def lsgan_fused(self, outs, nseg, targets, weights, loss_scale, grad_scale, loss_total, accumulate, loss_plain=None,
+                    want_grad=True):
+        """outs: patch maps [G, nseg*B, h, w, 1] of every scale; targets [nseg], weights [G][nseg] python floats.
+        loss_total[g] (+)= loss_scale * sum_maps sum_seg weights[g][seg] * mean_seg((out - target[seg])^2); returns the
+        gradients d(out) = grad_scale * weights[g][seg] * 2/n_seg * (out - target[seg]), one per map.  ONE launch."""
+        self._chk(loss_total, loss_plain, *outs)
+        G = outs[0].shape[0]
+        d = LsganDesc()
+        d.nmaps, d.G, d.nseg = len(outs), G, nseg
+        douts = [torch.empty_like(o) for o in outs] if want_grad else [None] * len(outs)
+        for m, o in enumerate(outs):
+            d.out[m], d.dout[m], d.n_per_seg[m] = _p(o), _p(douts[m]), o[0].numel() // nseg
+        for k in range(nseg):
+            d.target[k] = targets[k]
+        for g in range(G):
+            for k in range(nseg):
+                d.weight[g][k] = weights[g][k]
+        d.loss_scale, d.grad_scale = loss_scale, grad_scale
+        ws = self._loss_scratch(G)
+        self._ck(self.lib.cg_lsgan_fused(C.byref(d), _p(loss_total), int(bool(accumulate)), _p(loss_plain), _p(ws), ws.numel(),
+                                         self._stream()), 'cg_lsgan_fused')
+        return douts
+
+    def _gen_desc(self, adv_outs, cl_outs, mask, center, eps, adv_grad_scale, adv_douts=None, cl_douts=None):
+        d = GenLossDesc()
+        if mask is not None:
+            d.G, d.B, d.H, d.W, _ = mask.shape
+        elif adv_outs or cl_outs:
+            d.G = (adv_outs + cl_outs)[0].shape[0]
+        d.n_adv, d.n_cl = len(adv_outs), len(cl_outs)
+        for m, o in enumerate(adv_outs):
+            d.adv_out[m], d.adv_n[m] = _p(o), o[0].numel()
+            d.adv_dout[m] = _p(adv_douts[m]) if adv_douts else None
+        for m, o in enumerate(cl_outs):
+            d.cl_out[m], d.cl_n[m] = _p(o), o[0].numel()
+            d.cl_dout[m] = _p(cl_douts[m]) if cl_douts else None
+        d.mask = _p(mask)
+        d.center, d.eps, d.adv_grad_scale = center, eps, adv_grad_scale
+        return d
+
+    def gen_loss_fwd(self, adv_outs, cl_outs, mask, center, eps, adv_grad_scale, scal):
+        """Pass 1 of the generator loss: scal[G,6] = {adv, council, focus sums x4} of this rank in ONE launch; returns the
+        gradients of the adversarial patch maps (their coefficient gan_w * 2 / (n * world) does not depend on loss values)."""
+        self._chk(scal, mask, *adv_outs, *cl_outs)
+        adv_douts = [torch.empty_like(o) for o in adv_outs]
+        d = self._gen_desc(adv_outs, cl_outs, mask, center, eps, adv_grad_scale, adv_douts)
+        d.G = scal.shape[0]
+        ws = self._loss_scratch(d.G, d.B, d.H, d.W)
+        self._ck(self.lib.cg_gen_loss_fwd(C.byref(d), _p(scal), _p(ws), ws.numel(), self._stream()), 'cg_gen_loss_fwd')
+        return adv_douts
+
+    def gen_loss_bwd(self, cl_outs, mask, center, eps, scal, hp, hist_gan, hist_council, total, accumulate, pub, want_dmask):
+        """Pass 2: loss assembly, history matching and publication on the device + council-map / mask gradients, ONE launch.
+        hp: dict with the cg_gen_loss_hp fields.  Returns (cl_douts, d_mask or None)."""
+        self._chk(scal, mask, total, pub, *cl_outs)
+        assert hist_gan.dtype == torch.float64 and hist_council.dtype == torch.float64
+        cl_douts = [torch.empty_like(o) for o in cl_outs]
+        d = self._gen_desc([], cl_outs, mask, center, eps, 0.0, None, cl_douts)
+        d.G = total.shape[0]
+        h = GenLossHp()
+        for k, v in hp.items():
+            setattr(h, k, v)
+        d_mask = torch.empty_like(mask) if want_dmask else None
+        ws = self._loss_scratch(d.G, d.B, d.H, d.W)
+        self._ck(self.lib.cg_gen_loss_bwd(C.byref(d), C.byref(h), _p(scal), hist_gan.data_ptr(), hist_council.data_ptr(), _p(total),
+                                          int(bool(accumulate)), _p(pub), _p(d_mask), _p(ws), ws.numel(), self._stream()),
+                 'cg_gen_loss_bwd')
+        return cl_douts, d_mask
 
     # -- optimiser --------------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

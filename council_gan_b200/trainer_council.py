@@ -15,11 +15,15 @@ What is different underneath (B200-first):
   * forward and backward are explicit sequences of our own CUDA kernels; no autograd graph, no
     cuDNN/cuBLAS; the dead work the reference performs is skipped (style encoder :754/829/331, D/DC
     weight gradients inside gen_update, the second/third evaluation of the same content encoding);
-  * one host<->device synchronisation per gen_update (the loss-history matching :518-524,576-586 needs
-    the loss values on the host) instead of 2N;
+  * NO host<->device synchronisation inside an iteration: the losses of all scales, the focus terms, the
+    loss-history matching (:518-524,576-586: float64 ring buffers on the device) and every loss gradient are
+    three fused kernels (csrc/losses.cu); the published loss attributes are 0-d device tensors exactly like the
+    reference's, so the only sync is the one the caller makes when it reads them (write_loss, utils.py:277-305);
   * data parallel: when ``torch.distributed`` is initialised every rank holds all members, takes its
     slice of the global minibatch and the flat gradient buffer of each family is all-reduced (NCCL)
-    once per optimiser step.
+    once per optimiser step -- asynchronously: the discriminators' all-reduce + Adam are joined only when that
+    family's parameters are next needed (dis: during dis_council_update; dis_council: during gen_update's
+    generator forward; gen: decoder bucket during the encoder backward).
 Paths outside the live configuration space of the reference's three configs (recon_*/vgg/abs losses,
 nsgan/RaHinge, do_my_style, gray-scale D, random D/G pairing) raise NotImplementedError.
 """
@@ -45,10 +49,6 @@ def _dist():
     if dist.is_available() and dist.is_initialized():
         return dist
     return None
-
-
-class _LossList(list):
-    """List of 0-d tensors (what the reference publishes for write_loss, utils.py:277-305)."""
 
 
 class Council_Trainer(nn.Module):
@@ -96,9 +96,7 @@ class Council_Trainer(nn.Module):
         self._check_supported(hp)
         self._dirs = [d for d in _DIRS if hp['do_' + d]]
         N, hist = self.council_size, self.los_matching_hist_size_conf
-        for d in self._dirs:  # :70-92
-            setattr(self, 'los_hist_gan_%s_s' % d, [deque(np.ones(hist)) for _ in range(N)])
-            setattr(self, 'los_hist_council_%s_s' % d, [deque(np.ones(hist)) for _ in range(N)])
+        for d in self._dirs:  # :70-92; the gan / council histories live on the device (see _rings), these two are never updated
             setattr(self, 'los_hist_focus_%s_s' % d, [deque(np.ones(hist)) for _ in range(N)])
             setattr(self, 'los_hist_focus_zero_one_%s_s' % d, [deque(np.ones(hist)) for _ in range(N)])
         self.do_council_loss = None
@@ -108,6 +106,12 @@ class Council_Trainer(nn.Module):
             from .ops import CudaOps
             _ops = CudaOps(cuda_device)
         object.__setattr__(self, 'ops', _ops)
+        # loss histories of the matching (:81-92, deque(np.ones(hist))): float64 rings [N][hist+1] on the device, window start
+        # kept on the host; exported as deques by the los_hist_{gan,council}_{a2b,b2a}_s attributes
+        rings = {d: {'gan': torch.ones(N, hist + 1, dtype=torch.float64, device=_ops.device),
+                     'council': torch.ones(N, hist + 1, dtype=torch.float64, device=_ops.device),
+                     'head_gan': 0, 'head_council': 0} for d in self._dirs}
+        object.__setattr__(self, '_rings', rings)
         dist = _dist()
         self.world = dist.get_world_size() if dist else 1
         self.rank = dist.get_rank() if dist else 0
@@ -125,6 +129,7 @@ class Council_Trainer(nn.Module):
         if self.do_dis_council:
             self.dis_council_a2b_s, self.dis_council_b2a_s = [], []
         for name, net in nets.items():
+            net._before_access = self._flush
             object.__setattr__(self, name + '_s', [net.member(i) for i in range(N)])
         self.style_dim = hp['gen']['style_dim']
 
@@ -146,8 +151,39 @@ class Council_Trainer(nn.Module):
         self._img_cache = {}
         self._enc_cache = {}
         self._idx_cache = {}
-        self._const_cache = {}
+        self.img_cache_misses = 0  # image batches uploaded / converted (bench.py checks its e2e leg really copies)
+        object.__setattr__(self, '_pending', {})  # family -> [(net, bucket, async work)] awaiting all-reduce completion + Adam
         self.hyperparameters = hp
+        self.sync_parameters()
+
+    def __getattr__(self, name):
+        # los_hist_gan_a2b_s etc. (trainer_council.py:81-92): lists of deques, read back from the device rings on demand
+        if name.startswith('los_hist_gan_') or name.startswith('los_hist_council_'):
+            kind, d = ('gan', name[13:16]) if name.startswith('los_hist_gan_') else ('council', name[17:20])
+            rings = self.__dict__.get('_rings', {})
+            if d in rings and name.endswith('_s'):
+                r = rings[d]
+                R = r[kind].shape[1]
+                host = r[kind].detach().cpu().numpy()
+                head = r['head_' + kind]
+                return [deque(host[i, [(head + k) % R for k in range(R - 1)]]) for i in range(host.shape[0])]
+        return super().__getattr__(name)
+
+    def sync_parameters(self):
+        """Data parallel: every rank must hold the same parameters and optimiser state.  Only gradients are all-reduced
+        during training, so rank 0's banks are broadcast after construction / resume() (ranks seeded differently, e.g.
+        seed + rank, would otherwise train replicas that never re-synchronise).  No-op without a process group."""
+        dist = _dist()
+        if dist is None or self.world <= 1:
+            return
+        self._flush()
+        for net in self._nets.values():
+            for bank in net._banks():
+                dist.broadcast(bank.data, 0)
+                if bank.trainable:
+                    dist.broadcast(bank.exp_avg, 0)
+                    dist.broadcast(bank.exp_avg_sq, 0)
+            net.params_changed()
 
     # ------------------------------------------------------------------------------------------------
     @staticmethod
@@ -201,33 +237,27 @@ class Council_Trainer(nn.Module):
 
     # ---- small host/device helpers ---------------------------------------------------------------------
     def _img(self, x):
-        """NCHW image batch (any device) -> shared channels-last [1,B,H,W,4] on the device (cached per tensor)."""
+        """NCHW image batch (any device) -> shared channels-last [1,B,H,W,4] on the device.  Cached per tensor OBJECT (the
+        three updates of one iteration receive the same tensors, train.py:241-250); a new tensor is always uploaded."""
         key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
-        hit = self._img_cache.get('k')
-        if hit is not None and hit[0] == key:
-            return hit[1]
-        hit2 = self._img_cache.get('k2')
-        if hit2 is not None and hit2[0] == key:
-            return hit2[1]
+        for slot in ('k', 'k2'):
+            hit = self._img_cache.get(slot)
+            if hit is not None and hit[0] == key and hit[2] is x:
+                return hit[1]
         xd = x.detach().to(self.ops.device, self.ops.dtype, non_blocking=True).contiguous()
         img = self.ops.nchw_to_nhwc(xd, IMG_C)[None]
+        self.img_cache_misses += 1
         self._img_cache['k2'] = self._img_cache.get('k')
         self._img_cache['k'] = (key, img, x)
         return img
 
     def _noise(self, batch):
-        """torch.randn(B, style_dim, 1, 1) on the CPU generator (:284-285,741,744,807,809), moved to the device.
-        Under data parallelism the GLOBAL batch is drawn on every rank (same seed) and sliced."""
+        """torch.randn(B, style_dim, 1, 1) on the CPU generator (:284-285,741,744,807,809) as a HOST tensor [1,B,1,1,S];
+        ops.stage() moves it.  Under data parallelism the GLOBAL batch is drawn on every rank (all ranks must be seeded
+        identically: same torch / python `random` seeds) and sliced."""
         s = torch.randn(batch * self.world, self.style_dim, 1, 1)
         s = s[self.rank * batch:(self.rank + 1) * batch]
-        return s.reshape(1, batch, 1, 1, self.style_dim).to(self.ops.device, self.ops.dtype, non_blocking=True)
-
-    def _const(self, key, values):
-        t = self._const_cache.get(key)
-        if t is None:
-            t = torch.tensor(values, dtype=self.ops.dtype).to(self.ops.device)
-            self._const_cache[key] = t
-        return t
+        return s.reshape(1, batch, 1, 1, self.style_dim)
 
     def _idx(self, key, build):
         t = self._idx_cache.get(key)
@@ -254,32 +284,66 @@ class Council_Trainer(nn.Module):
             return self._lr0
         return self._lr0 * self._gamma ** (self._sched_epoch[fam] // self._step_size)
 
-    def _adam(self, fam):
-        """All-reduce the flat gradient of a family (data parallel) and run the fused Adam kernel on it."""
+    # ---- optimiser step, data-parallel gradient exchange ---------------------------------------------------
+    def _reduce_async(self, fam, net, lo=0, hi=None):
+        """Queue the all-reduce of grad[lo:hi] of one network (NCCL stream, ordered after everything issued so far)."""
         dist = _dist()
-        for d in self._dirs:
-            net = self._nets.get('%s_%s' % (fam, d))
-            if net is None:
-                continue
+        work = None
+        if dist is not None and self.world > 1:
+            g = net.bank.grad if (lo == 0 and hi is None) else net.bank.grad[lo:hi]
+            work = dist.all_reduce(g, async_op=True)  # SUM; local coefficients already carry 1/world
+        self._pending.setdefault(fam, []).append((net, work))
+
+    def _finish(self, fam):
+        """Join the family's queued all-reduces (stream-side wait, no host block on NCCL) and run its fused Adam."""
+        items = self._pending.pop(fam, None)
+        if not items:
+            return
+        if hasattr(self.ops, 'wgrad_join'):
+            self.ops.wgrad_join()  # weight gradients may have been queued on a side stream (COUNCIL_WGRAD_STREAM=1)
+        for _, work in items:
+            if work is not None:
+                work.wait()  # every bucket of the family first
+        done = []
+        for net, _ in items:
+            if any(net is n for n in done):
+                continue  # a network with several buckets steps once
+            done.append(net)
             bank = net.bank
-            if hasattr(self.ops, 'wgrad_join'):
-                self.ops.wgrad_join()  # weight gradients may have been queued on a side stream (COUNCIL_WGRAD_STREAM=1)
-            if dist is not None and self.world > 1:
-                dist.all_reduce(bank.grad)  # SUM; local coefficients already carry 1/world
             bank.step += 1
             self.ops.adam_step(bank.data, bank.grad, bank.exp_avg, bank.exp_avg_sq, self._lr(fam), self._betas[0],
                                self._betas[1], 1e-8, self._wd, bank.step)
             net.params_changed()
 
+    def _flush(self):
+        for fam in list(self._pending):
+            self._finish(fam)
+
+    def synchronize(self):
+        """Join every deferred optimiser step (data parallel: the gradient all-reduce of the last update is still in flight
+        when gen_update returns).  Called implicitly by the next update, save(), sample() and every state_dict access."""
+        self._flush()
+
+    def _adam(self, fam, defer=False):
+        """All-reduce the flat gradient of a family (data parallel) and run the fused Adam kernel on it.  defer: leave both
+        queued until the family's parameters are next needed (_finish), so that the all-reduce overlaps the next update."""
+        for d in self._dirs:
+            net = self._nets.get('%s_%s' % (fam, d))
+            if net is None:
+                continue
+            if not any(net is n for n, _ in self._pending.get(fam, [])):
+                self._reduce_async(fam, net)
+        if not (defer and self.world > 1):
+            self._finish(fam)
+
     def _src(self, d, a, b):
         return a if d == 'a2b' else b
 
-    def _global_mean(self, t):
-        """Reported loss values are means over the GLOBAL minibatch (equal shards): average over ranks."""
+    def _global_sum(self, t):
+        """Reported loss values are means over the GLOBAL minibatch (equal shards); the local values already carry 1/world."""
         dist = _dist()
         if dist is not None and self.world > 1:
             dist.all_reduce(t)
-            t = t / self.world
         return t
 
     # ==================================================================================================
@@ -288,61 +352,39 @@ class Council_Trainer(nn.Module):
     def dis_update(self, x_a=None, x_b=None, hyperparameters=None):
         hp = hyperparameters
         self._check_supported(hp)
+        self._flush()
         ops, N = self.ops, self.council_size
         img_a, img_b = self._img(x_a), self._img(x_b)
-        s = {}
+        noise = []
         if self.do_a2b_conf:  # :740-745
-            s['a2b'] = self._noise(x_b.size(0))
+            noise.append(('a2b', self._noise(x_b.size(0))))
         if self.do_b2a_conf:
-            s['b2a'] = self._noise(x_a.size(0))
-        total = ops.zeros(N)
-        self._dis_sums = {}
-        first = True
-        for d in self._dirs:
+            noise.append(('b2a', self._noise(x_a.size(0))))
+        s = dict(zip((k for k, _ in noise), ops.stage([v for _, v in noise])))
+        total = ops.empty(N)
+        inv_world = 1.0 / self.world
+        for di, d in enumerate(self._dirs):
             gen, dis = self._nets['gen_' + d], self._nets['dis_' + d]
             src, real = self._src(d, img_a, img_b), self._src(d, img_b, img_a)
             B, H, W = src.shape[1:4]
             c, _ = self._encode(d, src, save=True)
             x_fake, _ = gen.decode(c, s[d], src)
-            # D minibatch per member: [own fake ; real]   (calc_dis_loss networks.py:56-64)
-            pool = torch.cat((x_fake.view(N * B, H, W, IMG_C), real[0]), 0)
+            # D minibatch per member: [own fake ; real]   (calc_dis_loss networks.py:56-64); slots >= N*B read the real batch
             idx = self._idx(('dis', N, B), lambda: [[g * B + b for b in range(B)] + [N * B + b for b in range(B)]
                                                     for g in range(N)])
-            xin = ops.gather_images(pool, idx, None, N, 2 * B)
+            xin = ops.gather_images((x_fake.view(N * B, H, W, IMG_C), real[0]), idx, None, N, 2 * B)
             saved = []
             outs = dis.forward(xin, saved)
             wdir = float(hp['gan_w']) if d == 'a2b' else 1.0  # :775 vs :777 (no gan_w on the b2a branch)
-            targets = self._const('t01', [0.0, 1.0])
-            weights = self._const(('w2', wdir, N), [[wdir, wdir]] * N)
-            d_outs = []
-            self._dis_sums[d] = []
-            for out in outs:
-                n_seg = out[0].numel() // 2
-                sums = ops.lsgan_fwd(out, targets, weights, 2, total, accumulate=not first)
-                first = False
-                self._dis_sums[d].append((sums, n_seg))
-                cf = wdir * 2.0 / (n_seg * self.world)
-                coef = self._const(('c2', cf, N), [[cf, cf]] * N)
-                d_outs.append(ops.lsgan_bwd(out, targets, coef, 2))
+            plain = ops.empty(N)
+            # loss of both scales + d(loss)/d(out) = wdir * 2 / (n * world) * (out - target): one launch
+            d_outs = ops.lsgan_fused(outs, 2, [0.0, 1.0], [[wdir, wdir]] * N, inv_world, inv_world, total, di > 0, plain)
+            plain = self._global_sum(plain)
+            setattr(self, 'loss_dis_%s_s' % d, [plain[i] for i in range(N)])  # :765-768, only for active directions
             dis.backward(d_outs, saved, want_wgrad=True, want_dx=False)
-        total = self._global_mean(total)
-        self._loss_dis_total = total
-        self.loss_dis_total_s = _LossList(total[i] for i in range(N))
-        self._adam('dis')
-
-    def _per_dir_dis_loss(self, d):
-        tot = 0
-        for sums, n in self._dis_sums[d]:
-            tot = tot + sums.sum(-1) / n
-        return _LossList(tot[i] for i in range(self.council_size))
-
-    @property
-    def loss_dis_a2b_s(self):
-        return self._per_dir_dis_loss('a2b')
-
-    @property
-    def loss_dis_b2a_s(self):
-        return self._per_dir_dis_loss('b2a')
+        total = self._global_sum(total)
+        self.loss_dis_total_s = [total[i] for i in range(N)]
+        self._adam('dis', defer=True)  # joined when the D parameters are next needed (gen_update / the next dis_update)
 
     # ==================================================================================================
     # dis_council_update   (trainer_council.py:782-883)
@@ -357,13 +399,15 @@ class Council_Trainer(nn.Module):
         if not self.do_council_loss or hp['council_w'] == 0 or hp['iteration'] < cc['council_start_at_iter']:
             return
         self._check_supported(hp)
+        self._finish('dis_council')
+        self._finish('gen')
         ops, N = self.ops, self.council_size
         img_a, img_b = self._img(x_a), self._img(x_b)
-        s = {}
+        noise = []
         if self.do_b2a_conf:  # :806-809: s_a first, then s_b
-            s['b2a'] = self._noise(x_a.size(0))
+            noise.append(('b2a', self._noise(x_a.size(0))))
         if self.do_a2b_conf:
-            s['a2b'] = self._noise(x_b.size(0))
+            noise.append(('a2b', self._noise(x_b.size(0))))
         less = cc['discriminetro_less_style_by']
         # peers: python `random`, without replacement, pool refilled when exhausted (:861-868)
         Kcfg = cc['numberOfCouncil_dis_relative_iteration']
@@ -387,45 +431,42 @@ class Council_Trainer(nn.Module):
         Krun = len(peers[0])
         U = len(uniq[0])
         assert all(len(u) == U for u in uniq)
-        total = ops.zeros(N)
-        first = True
-        for d in self._dirs:
+        # every small host table of this update (style noise, less-style noise, slot tables) goes up in ONE pinned copy
+        Bs = {d: self._src(d, img_a, img_b).shape[1] for d in self._dirs}
+        comp0 = {d: (N * Bs[d] if less != 0 else 0) for d in self._dirs}
+        tables = [torch.tensor([[g * Bs[d] + b for b in range(Bs[d])] +
+                                [comp0[d] + j * Bs[d] + b for j in uniq[g] for b in range(Bs[d])] for g in range(N)], dtype=torch.int32)
+                  for d in self._dirs]
+        host = [v for _, v in noise] + ([v * less for _, v in noise] if less != 0 else []) + tables
+        dev = ops.stage(host)
+        s = dict(zip((k for k, _ in noise), dev[:len(noise)]))
+        s_less = dict(zip((k for k, _ in noise), dev[len(noise):2 * len(noise)])) if less != 0 else {}
+        idx = dict(zip(self._dirs, dev[-len(self._dirs):]))
+        total = ops.empty(N)
+        inv_world = 1.0 / self.world
+        for di, d in enumerate(self._dirs):
             gen, disc = self._nets['gen_' + d], self._nets['dis_council_' + d]
             src = self._src(d, img_a, img_b)
             B, H, W = src.shape[1:4]
             c, _ = self._encode(d, src, save=True)
             x_fake, _ = gen.decode(c, s[d], src)
+            pools = [x_fake.view(N * B, H, W, IMG_C)]
             if less != 0:
-                x_less, _ = gen.decode(c, s[d] * less, src)
-                pool = torch.cat((x_fake.view(N * B, H, W, IMG_C), x_less.view(N * B, H, W, IMG_C)), 0)
-                comp0 = N * B
-            else:
-                pool = x_fake.view(N * B, H, W, IMG_C)
-                comp0 = 0
-            idx = torch.tensor([[g * B + b for b in range(B)] +
-                                [comp0 + j * B + b for j in uniq[g] for b in range(B)] for g in range(N)],
-                               dtype=torch.int32).to(ops.device, non_blocking=True)
-            xin = ops.gather_images(pool, idx, src, N, (1 + U) * B)
+                x_less, _ = gen.decode(c, s_less[d], src)
+                pools.append(x_less.view(N * B, H, W, IMG_C))
+            if di == 0:
+                self._finish('dis')  # dis_update's all-reduce had the generator decodes above to complete behind
+            xin = ops.gather_images(pools, idx[d], src, N, (1 + U) * B)
             saved = []
             outs = disc.forward(xin, saved)
             # sum_k [ mean(D(fake_i)^2) + mean((D(less_jk)-1)^2) ] * council_w / Kcfg   (:872, :878)
             wk = float(hp['council_w']) / Kcfg
-            targets = self._const(('t0k', U), [0.0] + [1.0] * U)
             wrows = [[wk * Krun] + [wk * m for m in mult[g]] for g in range(N)]
-            weights = torch.tensor(wrows, dtype=ops.dtype).to(ops.device, non_blocking=True)
-            d_outs = []
-            for out in outs:
-                n_seg = out[0].numel() // (1 + U)
-                ops.lsgan_fwd(out, targets, weights, 1 + U, total, accumulate=not first)
-                first = False
-                cf = 2.0 / (n_seg * self.world)
-                coef = torch.tensor([[v * cf for v in row] for row in wrows], dtype=ops.dtype).to(ops.device, non_blocking=True)
-                d_outs.append(ops.lsgan_bwd(out, targets, coef, 1 + U))
+            d_outs = ops.lsgan_fused(outs, 1 + U, [0.0] + [1.0] * U, wrows, inv_world, inv_world, total, di > 0)
             disc.backward(d_outs, saved, want_wgrad=True, want_dx=False)
-        total = self._global_mean(total)
-        self._loss_dis_council_total = total
-        self.loss_dis_council_total_s = _LossList(total[i] for i in range(N))
-        self._adam('dis_council')
+        total = self._global_sum(total)
+        self.loss_dis_council_total_s = [total[i] for i in range(N)]
+        self._adam('dis_council', defer=True)  # joined before gen_update evaluates the council discriminators
 
     # ==================================================================================================
     # gen_update   (trainer_council.py:280-634)
@@ -434,11 +475,13 @@ class Council_Trainer(nn.Module):
         hp = hyperparameters
         self.hyperparameters = hp
         self._check_supported(hp)
+        self._finish('gen')
         ops, N = self.ops, self.council_size
         fl = hp['focus_loss']
         img_a, img_b = self._img(x_a), self._img(x_b)
         s_a = self._noise(x_a.size(0))  # :284-285 both are always drawn, a first
         s_b = self._noise(x_b.size(0))
+        s_a, s_b = ops.stage([s_a, s_b])
         s = {'a2b': s_b, 'b2a': s_a}
         it = hp['iteration']
         focus_gate = it > fl['focus_loss_start_at_iter']
@@ -453,155 +496,96 @@ class Council_Trainer(nn.Module):
         self.do_council_loss = self._gate(hp, for_gen=True)
         council_on = (hp['council_w'] != 0) and self.do_council_loss and N > 1 and self.do_dis_council  # :559,567
         gan_on = hp['gan_w'] != 0
+        center, eps = float(fl['mask_zero_or_one_center']), float(fl['mask_zero_or_one_epsilon'])
 
+        # ---- forward of every direction; pass 1 of the loss (all reductions, one launch per direction) -----------
         fw = {}
-        scal = []  # device scalars to bring to the host in ONE copy: per dir [adv(N), council(N), focus(N,4)]
-        for d in self._dirs:
+        scal = ops.empty(len(self._dirs), N, 6)  # per direction and member: [adv, council, focus sums x4] of THIS rank
+        for di, d in enumerate(self._dirs):
             gen = self._nets['gen_' + d]
             src = self._src(d, img_a, img_b)
             B, H, W = src.shape[1:4]
             c, enc_saved = self._encode(d, src, save=True)
             dec_saved = []
             x_fake, mask = gen.decode(c, s[d], src, dec_saved)
-            rec = {'enc': enc_saved, 'dec': dec_saved, 'x_fake': x_fake, 'mask': mask, 'B': B, 'H': H, 'W': W}
-            adv = ops.zeros(N)
-            cl = ops.zeros(N)
-            fs = ops.zeros(N, 4)
-            ones = self._const('t1', [1.0])
-            onesw = self._const(('w1', N), [[1.0]] * N)
+            rec = {'enc': enc_saved, 'dec': dec_saved, 'x_fake': x_fake, 'mask': mask, 'B': B, 'H': H, 'W': W,
+                   'dis_outs': [], 'disc_outs': []}
             if gan_on:  # calc_gen_loss networks.py:84-90
+                if di == 0:
+                    self._finish('dis')
                 rec['dis_saved'] = []
                 rec['dis_outs'] = self._nets['dis_' + d].forward(x_fake, rec['dis_saved'])
-                for k, out in enumerate(rec['dis_outs']):
-                    ops.lsgan_fwd(out, ones, onesw, 1, adv, accumulate=k > 0)
             if council_on:  # MsImageDisCouncil.calc_gen_loss networks.py:188-194
+                if di == 0:
+                    self._finish('dis_council')
                 idx = self._idx(('id', N, B), lambda: [[g * B + b for b in range(B)] for g in range(N)])
                 xin = ops.gather_images(x_fake.view(N * B, H, W, IMG_C), idx, src, N, B)
                 rec['disc_saved'] = []
                 rec['disc_outs'] = self._nets['dis_council_' + d].forward(xin, rec['disc_saved'])
-                for k, out in enumerate(rec['disc_outs']):
-                    ops.lsgan_fwd(out, ones, onesw, 1, cl, accumulate=k > 0)
-            if focus_on:
-                fs = ops.focus_fwd(mask, fl['mask_zero_or_one_center'], fl['mask_zero_or_one_epsilon'])
+            rec['d_adv'] = ops.gen_loss_fwd(rec['dis_outs'], rec['disc_outs'], mask if focus_on else None, center, eps,
+                                            float(hp['gan_w']) / self.world, scal[di])
             fw[d] = rec
-            scal.append(torch.cat((adv.view(N, 1), cl.view(N, 1), fs), 1))
-        dev_scal = torch.stack(scal)  # [ndirs, N, 6]
+        self._flush()  # (a family gated off above still steps here)
         dist = _dist()
         if dist is not None and self.world > 1:
-            dist.all_reduce(dev_scal)  # sums over ranks; means are divided by world below
-        host = dev_scal.cpu().double().numpy()  # the one host sync of gen_update
+            dist.all_reduce(scal)  # sums over ranks; pass 2 divides the means by world and uses the GLOBAL (sum m / numel)^2
 
-        # ---- host: loss values, history matching, backward coefficients --------------------------------
-        tot = np.zeros(N, dtype=np.float64)
-        names = {}
-        coefs = {}
+        # ---- pass 2 (loss assembly + history matching on the device, remaining loss gradients) and the backward ------
+        total = ops.empty(N)
+        pub = ops.empty(len(self._dirs), N, 8)
+        matching = bool(self.do_w_loss_matching)
         for di, d in enumerate(self._dirs):
-            ab = 'ab' if d == 'a2b' else 'ba'
-            rec = fw[d]
-            numel = rec['B'] * self.world * 3 * rec['H'] * rec['W']  # mask.numel() of the GLOBAL batch
-            adv = host[di, :, 0] / self.world
-            cl = host[di, :, 1] / self.world
-            f = host[di, :, 2:]
-            l01 = f[:, 0] / numel
-            msum = f[:, 1] / numel
-            ltv = (f[:, 2] + f[:, 3]) / numel
-            ltot = np.zeros(N)
-            c01 = csum = ctv = np.zeros(N)
-            z01, ztot, ztv = [], [0] * N, [0] * N
-            if focus_on:
-                if hp['mask_zero_or_one_w'] != 0:  # :392-415
-                    z01 = list(l01)
-                    tot += hp['mask_zero_or_one_w'] * l01
-                    c01 = np.full(N, hp['mask_zero_or_one_w'] / numel)
-                if hp['mask_tv_w'] != 0:  # :425-431
-                    ztv = list(ltv)
-                    tot += hp['mask_tv_w'] * ltv
-                    ctv = np.full(N, hp['mask_tv_w'] / numel)
-                if hp['mask_total_w'] != 0:  # :418-422 then :447-451
-                    csum = np.zeros(N)
-                    if fl['mask_small_use_abs']:
-                        ltot = ltot + np.abs(msum)
-                        csum = csum + hp['mask_total_w'] * np.sign(msum) / numel
-                    if fl['mask_small_use_square']:
-                        ltot = ltot + msum ** 2
-                        csum = csum + hp['mask_total_w'] * 2.0 * msum / numel
-                    ztot = list(ltot)
-                    tot += hp['mask_total_w'] * ltot
-            hist_gan = getattr(self, 'los_hist_gan_%s_s' % d)
-            hist_c = getattr(self, 'los_hist_council_%s_s' % d)
-            if gan_on:
-                if self.do_w_loss_matching:  # :518-524
-                    for i in range(N):
-                        hist_gan[i].append(np.float32(adv[i]))
-                        hist_gan[i].popleft()
-                tot += hp['gan_w'] * adv
-            cdis = np.zeros(N)
-            closs = [0] * N
-            if council_on:
-                w = np.ones(N)
-                if self.do_w_loss_matching:  # :576-586
-                    for i in range(N):
-                        hist_c[i].append(np.float32(cl[i]))
-                        hist_c[i].popleft()
-                        w[i] = np.mean(hist_gan[i]) / np.mean(hist_c[i])
-                        setattr(self, 'w_match_%s_conf' % d, w[i])
-                closs_v = cl * w.astype(np.float32) * hp['council_w']
-                closs = list(closs_v)
-                tot += closs_v
-                cdis = w * hp['council_w']
-            names[d] = (ab, adv, z01, ztot, ztv, closs)
-            coefs[d] = (c01, csum, ctv, cdis)
-
-        # ---- backward --------------------------------------------------------------------------------
-        for d in self._dirs:
             rec = fw[d]
             gen = self._nets['gen_' + d]
-            c01, csum, ctv, cdis = coefs[d]
-            ones = self._const('t1', [1.0])
+            ring = self._rings[d]
+            hpd = {'world': self.world, 'hist_size': self.los_matching_hist_size_conf, 'head_gan': ring['head_gan'],
+                   'head_council': ring['head_council'], 'gan_on': int(gan_on), 'council_on': int(council_on),
+                   'focus_on': int(focus_on), 'matching': int(matching), 'small_abs': int(bool(fl['mask_small_use_abs'])),
+                   'small_square': int(bool(fl['mask_small_use_square'])), 'gan_w': float(hp['gan_w']),
+                   'council_w': float(hp['council_w']), 'w01': float(hp['mask_zero_or_one_w']), 'wtot': float(hp['mask_total_w']),
+                   'wtv': float(hp['mask_tv_w']), 'numel': float(rec['B'] * self.world * 3 * rec['H'] * rec['W'])}
+            d_cl, d_mask = ops.gen_loss_bwd(rec['disc_outs'], rec['mask'] if focus_on else None, center, eps, scal[di], hpd,
+                                            ring['gan'], ring['council'], total, di > 0, pub[di], focus_on)
+            R = self.los_matching_hist_size_conf + 1
+            if gan_on and matching:  # :518-524 append + popleft
+                ring['head_gan'] = (ring['head_gan'] + 1) % R
+            if council_on and matching:  # :576-586
+                ring['head_council'] = (ring['head_council'] + 1) % R
             d_x = None
             if gan_on:
-                d_outs = []
-                for out in rec['dis_outs']:
-                    cf = hp['gan_w'] * 2.0 / (out[0].numel() * self.world)
-                    coef = self._const(('c1', cf, N), [[cf]] * N)
-                    d_outs.append(ops.lsgan_bwd(out, ones, coef, 1))
-                d_x = self._nets['dis_' + d].backward(d_outs, rec['dis_saved'], want_wgrad=False, want_dx=True)
+                d_x = self._nets['dis_' + d].backward(rec['d_adv'], rec['dis_saved'], want_wgrad=False, want_dx=True)
             if council_on:
-                d_outs = []
-                for out in rec['disc_outs']:
-                    cf = 2.0 / (out[0].numel() * self.world)
-                    coef = torch.tensor((cdis * cf).reshape(N, 1), dtype=ops.dtype).to(ops.device, non_blocking=True)
-                    d_outs.append(ops.lsgan_bwd(out, ones, coef, 1))
-                d_x8 = self._nets['dis_council_' + d].backward(d_outs, rec['disc_saved'], want_wgrad=False, want_dx=True)
+                d_x8 = self._nets['dis_council_' + d].backward(d_cl, rec['disc_saved'], want_wgrad=False, want_dx=True)
                 if d_x is None:
                     d_x = ops.zeros(*rec['x_fake'].shape)
                 ops.acc_slice(d_x, d_x8, 4)
             if d_x is None:
                 d_x = ops.zeros(*rec['x_fake'].shape)
-            d_mask = None
-            if focus_on:
-                coef = torch.tensor(np.stack((c01, csum, ctv), 1), dtype=ops.dtype).to(ops.device, non_blocking=True)
-                d_mask = ops.focus_bwd(rec['mask'], coef, fl['mask_zero_or_one_center'], fl['mask_zero_or_one_epsilon'])
-            gen.backward(d_x, d_mask, rec['enc'], rec['dec'])
-        self._adam('gen')
+            gen.backward(d_x, d_mask, rec['enc'], rec['dec'],
+                         on_decoder_done=(lambda g=gen: self._reduce_async('gen', g, g.enc_end, None)) if self.world > 1 else None)
+            if self.world > 1:
+                self._reduce_async('gen', gen, 0, gen.enc_end)  # encoder bucket; the decoder bucket went out during the encoder backward
+        self._adam('gen', defer=True)  # joined at the start of the next update (or by save / state_dict / sample)
         self._enc_cache.clear()
 
-        # ---- publish the reference's loss attributes (:302-322, :556-557) --------------------------------
-        def lst(v):
-            return _LossList(torch.tensor(float(x)) for x in v)
-        self.loss_gen_total_s = lst(tot)
+        # ---- publish the reference's loss attributes (:302-322, :556-557): 0-d DEVICE tensors, no sync here -------------
+        self.loss_gen_total_s = [total[i] for i in range(N)]
         for d in _DIRS:
             ab = 'ab' if d == 'a2b' else 'ba'
-            a2b = d
-            if d in names:
-                _, adv, z01, ztot, ztv, closs = names[d]
-                setattr(self, 'loss_gen_adv_%s_s' % a2b, lst(adv) if gan_on else [])
-                setattr(self, 'loss_gen_mask_zero_one_%s_s' % ab, lst(z01))
-                setattr(self, 'loss_gen_mask_total_%s_s' % ab, lst(ztot))
-                setattr(self, 'loss_gen_mask_TV_%s_s' % ab, lst(ztv))
-                setattr(self, 'council_loss_%s_s' % ab, lst(closs))
+            if d in fw:
+                di = self._dirs.index(d)
+
+                def col(k, on=True):
+                    return [pub[di, i, k] for i in range(N)] if on else []
+                setattr(self, 'loss_gen_adv_%s_s' % d, col(1, gan_on))
+                setattr(self, 'loss_gen_mask_zero_one_%s_s' % ab, col(2, focus_on and hp['mask_zero_or_one_w'] != 0))
+                setattr(self, 'loss_gen_mask_total_%s_s' % ab, col(3) if focus_on and hp['mask_total_w'] != 0 else [0] * N)
+                setattr(self, 'loss_gen_mask_TV_%s_s' % ab, col(4) if focus_on and hp['mask_tv_w'] != 0 else [0] * N)
+                setattr(self, 'council_loss_%s_s' % ab, col(5) if council_on else [0] * N)
+                if council_on and matching:
+                    setattr(self, 'w_match_%s_conf' % d, pub[di, N - 1, 6])  # the reference keeps the last member's ratio (:583)
             else:
-                setattr(self, 'loss_gen_adv_%s_s' % a2b, [0] * N if gan_on else [])
+                setattr(self, 'loss_gen_adv_%s_s' % d, [0] * N if gan_on else [])
                 setattr(self, 'loss_gen_mask_zero_one_%s_s' % ab, [])
                 setattr(self, 'loss_gen_mask_total_%s_s' % ab, [])
                 setattr(self, 'loss_gen_mask_TV_%s_s' % ab, [])
@@ -619,32 +603,40 @@ class Council_Trainer(nn.Module):
             self._sched_epoch[fam] += 1
 
     def sample(self, x_a=None, x_b=None, s_a=None, s_b=None, council_member_to_sample_vec=None, return_mask=True):
-        """Eval-mode translation of every image by every member (:643-733): returns the same 8-tuple."""
-        members = range(self.council_size) if council_member_to_sample_vec is None else council_member_to_sample_vec
+        """Translation of every image by every member (:643-733): returns the same 8-tuple, rows ordered image-major /
+        member-minor like the reference's double loop.  All members and all images run as ONE stacked pass per network
+        (the reference runs batch-1 passes in a Python double loop); instance norm / AdaIN are per-sample, so the result
+        per image is the same.  (eval() == train() for this network: no dropout, no running statistics.)"""
+        self._flush()
+        ops, N = self.ops, self.council_size
+        members = list(range(N)) if council_member_to_sample_vec is None else list(council_member_to_sample_vec)
         res = {}
         for d in _DIRS:
             if not getattr(self, 'do_%s_conf' % d):
                 res[d] = (None, None, None, None)
                 continue
             x = x_a if d == 'a2b' else x_b
+            B = x.size(0)
             fixed = (self.s_b if s_b is None else s_b) if d == 'a2b' else (self.s_a if s_a is None else s_a)
-            s2 = torch.randn(x.size(0), self.style_dim, 1, 1).to(self.ops.device)
-            gens = getattr(self, 'gen_%s_s' % d)
-            xs, second, first, third = [], [], [], []
-            for i in range(x.size(0)):
-                xi = x[i].unsqueeze(0)
-                for j in members:
-                    xs.append(xi.to(self.ops.device))
-                    c, s_fake = gens[j].encode(xi)
-                    if not return_mask:
-                        second.append(gens[j].decode(c, s_fake, xi))
-                        first.append(gens[j].decode(c, fixed[i].unsqueeze(0), xi))
-                    else:
-                        o, m = gens[j].decode(c, fixed[i].unsqueeze(0), xi, return_mask=True)
-                        second.append(m)
-                        first.append(o)
-                    third.append(gens[j].decode(c, s2[i].unsqueeze(0), xi))
-            res[d] = (torch.cat(xs), torch.cat(second), torch.cat(first), torch.cat(third))
+            s2 = torch.randn(B, self.style_dim, 1, 1)  # :649 / :655
+            gen = self._nets['gen_' + d]
+            img = ops.nchw_to_nhwc(x.detach().to(ops.device, ops.dtype).contiguous(), IMG_C)[None]
+
+            def st(t):  # [B, S, 1, 1] -> shared style [1, B, 1, 1, S]
+                return t[:B].to(ops.device, ops.dtype).reshape(1, B, 1, 1, self.style_dim).contiguous()
+            c = gen.encode(img)
+            first, mask1 = gen.decode(c, st(fixed), img)
+            third, _ = gen.decode(c, st(s2), img)
+            if return_mask:
+                second = mask1
+            else:
+                second, _ = gen.decode(c, gen.style_encode(img), img)  # recon with each member's own style code
+
+            def rows(t):  # [N, B, H, W, 4] -> [B * len(members), 3, H, W], image-major
+                t = ops.nhwc_to_nchw(t, 3)[members]
+                return t.permute(1, 0, 2, 3, 4).reshape(B * len(members), 3, t.shape[-2], t.shape[-1])
+            xs = x.detach().to(ops.device, ops.dtype).repeat_interleave(len(members), dim=0)
+            res[d] = (xs, rows(second), rows(first), rows(third))
         return res['a2b'] + res['b2a']
 
     def forward(self, *args, **kwargs):
@@ -652,7 +644,9 @@ class Council_Trainer(nn.Module):
                                   'references a nonexistent self.gen_a2b); use sample()')
 
     def save(self, snapshot_dir, iterations):
-        """Per-member checkpoint files with the reference's names and keys (:969-992)."""
+        """Per-member checkpoint files with the reference's names, keys and optimiser layout (:969-992): the reference's
+        resume() loads them, and ours loads the reference's."""
+        self._flush()
         for i in range(self.council_size):
             for fam in ('gen', 'dis', 'dis_council'):
                 if fam == 'dis_council' and not self.do_dis_council:
@@ -660,24 +654,67 @@ class Council_Trainer(nn.Module):
                 for d in self._dirs:
                     name = os.path.join(snapshot_dir, '%s_%s_%d_%08d.pt' % (d, fam, i, iterations + 1))
                     torch.save({d: getattr(self, '%s_%s_s' % (fam, d))[i].state_dict()}, name)
-            opt = {}
-            for fam in ('gen', 'dis', 'dis_council'):
-                if fam == 'dis_council' and not self.do_dis_council:
-                    continue
-                opt[fam] = {d: self._opt_state(fam, d, i) for d in self._dirs}
+            opt = {fam: self._opt_state_dict(fam, i) for fam in ('gen', 'dis', 'dis_council')
+                   if fam != 'dis_council' or self.do_dis_council}
             torch.save(opt, os.path.join(snapshot_dir, 'optimizer_%d.pt' % i))
 
-    def _opt_state(self, fam, d, i):
-        bank = self._nets['%s_%s' % (fam, d)].bank
-        sl = {}
-        for name, (off, shape, n) in bank.table.items():
-            per = n // bank.G
-            sl[name] = {'exp_avg': bank.exp_avg[off + i * per: off + (i + 1) * per].clone().cpu(),
-                        'exp_avg_sq': bank.exp_avg_sq[off + i * per: off + (i + 1) * per].clone().cpu()}
-        return {'step': bank.step, 'state': sl, 'sched_epoch': self._sched_epoch[fam]}
+    def _opt_params(self, fam):
+        """The parameter list of the reference's per-member optimiser (:152-179): a2b network then b2a network, each in
+        nn.Module.parameters() order (= state_dict order without buffers).  -> [(net, spec, is_weight)]"""
+        out = []
+        for d in self._dirs:
+            net = self._nets['%s_%s' % (fam, d)]
+            by_key = {}
+            for spec in net._specs():
+                by_key[spec.wname] = (net, spec, True)
+                by_key[spec.bname] = (net, spec, False)
+            out += [by_key[k] for k in net.reference_key_order() if k in by_key]
+        return out
+
+    def _opt_state_dict(self, fam, i):
+        """torch.optim.Adam.state_dict() of member i's optimiser for one family, from the flat moment buffers.
+        Parameters that never receive a gradient (the style encoder) have no state entry, as in the reference."""
+        state = {}
+        plist = self._opt_params(fam)
+        for idx, (net, spec, is_w) in enumerate(plist):
+            name = spec.wname if is_w else spec.bname
+            bank = net._bank_of(name)
+            if not bank.trainable or bank.step == 0:
+                continue
+            m, v = bank._view(bank.exp_avg, name)[i], bank._view(bank.exp_avg_sq, name)[i]
+            if is_w:
+                m, v = spec.export_weight(m), spec.export_weight(v)
+            state[idx] = {'step': torch.tensor(float(bank.step)), 'exp_avg': m.detach().clone().cpu(),
+                          'exp_avg_sq': v.detach().clone().cpu()}
+        group = {'lr': self._lr(fam), 'betas': tuple(self._betas), 'eps': 1e-8, 'weight_decay': self._wd, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'decoupled_weight_decay': False, 'initial_lr': self._lr0, 'params': list(range(len(plist)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def _load_opt_state_dict(self, fam, i, sd):
+        """Inverse of _opt_state_dict; accepts what torch.optim.Adam.state_dict() of the reference wrote (:988-992)."""
+        plist = self._opt_params(fam)
+        steps = []
+        for idx, ent in sd.get('state', {}).items():
+            net, spec, is_w = plist[int(idx)]
+            name = spec.wname if is_w else spec.bname
+            bank = net._bank_of(name)
+            if not bank.trainable:
+                continue
+            for key, buf in (('exp_avg', bank.exp_avg), ('exp_avg_sq', bank.exp_avg_sq)):
+                dst = bank._view(buf, name)[i]
+                if is_w:
+                    spec.import_weight(dst, ent[key])
+                else:
+                    dst.copy_(ent[key].detach().to('cpu', dst.dtype).reshape(-1))
+            steps.append(int(float(ent['step'])))
+        if steps:
+            for d in self._dirs:
+                self._nets['%s_%s' % (fam, d)].bank.step = max(steps)
 
     def resume(self, checkpoint_dir, hyperparameters):
         """Load the latest per-member checkpoints (:898-967); returns the iteration parsed from the file name."""
+        self._flush()
         iterations = 0
         for i in range(self.council_size):
             for fam in ('gen', 'dis', 'dis_council'):
@@ -696,24 +733,19 @@ class Council_Trainer(nn.Module):
                 if fam == 'gen':
                     iterations = int(last[-11:-3])
             opt_path = os.path.join(checkpoint_dir, 'optimizer_%d.pt' % i)
-            if os.path.exists(opt_path):
+            try:
                 opt = torch.load(opt_path, map_location='cpu')
-                for fam, per_dir in opt.items():
-                    for d, st in per_dir.items():
-                        if not isinstance(st, dict) or 'state' not in st:
-                            continue  # a reference-format optimizer file: moments restart from zero
-                        bank = self._nets['%s_%s' % (fam, d)].bank
-                        bank.step = st['step']
-                        self._sched_epoch[fam] = st.get('sched_epoch', iterations)
-                        for name, (off, shape, n) in bank.table.items():
-                            per = n // bank.G
-                            bank.exp_avg[off + i * per: off + (i + 1) * per].copy_(st['state'][name]['exp_avg'])
-                            bank.exp_avg_sq[off + i * per: off + (i + 1) * per].copy_(st['state'][name]['exp_avg_sq'])
+                for fam in ('dis', 'gen') + (('dis_council',) if self.do_dis_council else ()):
+                    self._load_opt_state_dict(fam, i, opt[fam])
+            except Exception as e:  # the reference warns and carries on as well (:958-959)
+                import warnings
+                warnings.warn('some optimizer FAILED to load (%s: %s): Adam moments restart from zero' % (type(e).__name__, e))
         if iterations > 0:
             print('Resume from iteration %d' % iterations)
-            for fam in self._sched_epoch:
-                self._sched_epoch[fam] = max(self._sched_epoch[fam], iterations)
+            for fam in self._sched_epoch:  # get_scheduler(..., last_epoch=iterations) :953-957
+                self._sched_epoch[fam] = iterations
         else:
             import warnings
             warnings.warn('FAILED TO RESUME STARTED FROM 0')
+        self.sync_parameters()
         return iterations

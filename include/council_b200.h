@@ -124,10 +124,12 @@ int cg_avgpool_bwd(const float* dy, float* dx, int N, int H, int W, int Cy, int 
                    int accumulate, void* stream);
 /* dst[n][..][0:nch] += src[n][..][0:nch]  (pixel counts equal) */
 int cg_acc_slice(float* dst, const float* src, long npix, int Cd, int Cs, int nch, void* stream);
-/* y[g][n] = pool[idx[g*Bt+n]] (4 lanes) ++ x_in[n % B] (4 lanes, if x_in != NULL -> 8-lane output):
- * builds discriminator minibatches (fake ++ real; torch.cat((x, x_input),1) networks.py:152). */
-int cg_gather_images(const float* pool, const int32_t* idx, const float* x_in, float* y, int G,
-                     int Bt, int B, int HW, void* stream);
+/* y[g][n] = slot(idx[g*Bt+n]) (4 lanes) ++ x_in[n % B] (4 lanes, if x_in != NULL -> 8-lane output), where
+ * slot(k) = k < n0 ? pool0[k] : pool1[k - n0]  (pool1 may be NULL when every index is < n0):
+ * builds discriminator minibatches without materialising torch.cat((fake, real)) (networks.py:56-64) or
+ * torch.cat((x, x_input), 1) (networks.py:152). */
+int cg_gather_images(const float* pool0, int n0, const float* pool1, const int32_t* idx, const float* x_in, float* y,
+                     int G, int Bt, int B, int HW, void* stream);
 /* NCHW [N][C][HW] <-> channels-last [N][HW][Cp] (Cp >= C, pad lanes zeroed) */
 int cg_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, void* stream);
 int cg_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int Cp, void* stream);
@@ -147,6 +149,58 @@ int cg_focus_fwd(const float* mask, float* sums, int G, int B, int H, int W, flo
 /* dmask = coef[g][0]*d(zero_one term) + coef[g][1]*d(sum m) + coef[g][2]*d(TV sums) */
 int cg_focus_bwd(const float* mask, const float* coef, float* dmask, int G, int B, int H, int W,
                  float center, float eps, void* stream);
+
+/* ---- fused losses (one launch per discriminator update and direction; two per gen_update and direction) ----------
+ * These replace the four calls above on the training path: the loss of EVERY discriminator scale, the focus terms, the
+ * loss-history matching and all their gradients, with no host round trip (trainer_council.py:518-524,576-586 run on the
+ * device).  `ws`: >= cg_loss_workspace_bytes() bytes, ZERO-INITIALISED once by the caller, not shared between streams;
+ * every call leaves its first 16 bytes (a ticket counter) zero again. */
+#define CG_LOSS_MAX_MAPS 4
+#define CG_LOSS_MAX_G 8
+#define CG_LOSS_MAX_SEG 8
+typedef struct {
+    int32_t nmaps, G, nseg, _pad;             /* patch maps (discriminator scales), members, segments per member */
+    const float* out[CG_LOSS_MAX_MAPS];       /* out[m][G][nseg][n_per_seg[m]]                                      */
+    float* dout[CG_LOSS_MAX_MAPS];            /* gradient of the same shape (NULL: not wanted)                      */
+    int32_t n_per_seg[CG_LOSS_MAX_MAPS];
+    float target[CG_LOSS_MAX_SEG];            /* 0 for generated, 1 for real / less-style segments                  */
+    float weight[CG_LOSS_MAX_G][CG_LOSS_MAX_SEG];
+    float loss_scale, grad_scale;             /* 1/world under data parallelism                                     */
+} cg_lsgan_desc;
+/* loss_total[g] (+)= loss_scale * sum_m sum_s weight[g][s] * mean((out-target[s])^2);   loss_plain[g] (NULL: skip) = the
+ * same with unit weights;   dout = grad_scale * weight[g][s] * 2/n_per_seg * (out - target[s]).
+ * calc_dis_loss networks.py:56-64,158-166 for all scales at once, with its autograd. */
+int cg_lsgan_fused(const cg_lsgan_desc* d, float* loss_total, int accumulate, float* loss_plain, void* ws,
+                   size_t ws_bytes, void* stream);
+
+typedef struct {
+    int32_t G, B, H, W;                       /* mask[G][B][H][W][4]; B = this rank's batch                         */
+    int32_t n_adv, n_cl;                      /* scales of MsImageDis / MsImageDisCouncil evaluated on x_fake (0..2) */
+    const float* adv_out[2]; float* adv_dout[2];   /* [G][adv_n]; gradient written by pass 1 (constant coefficient)  */
+    const float* cl_out[2];  float* cl_dout[2];    /* [G][cl_n];  gradient written by pass 2 (needs w_match)         */
+    int32_t adv_n[2], cl_n[2];
+    const float* mask;                        /* NULL: no focus terms                                               */
+    float center, eps, adv_grad_scale, _pad;  /* d adv_out = adv_grad_scale * 2/adv_n * (out-1): gan_w / world       */
+} cg_gen_loss_desc;
+typedef struct {
+    int32_t world, hist_size, head_gan, head_council;   /* history rings double[G][hist_size+1], window starts at head */
+    int32_t gan_on, council_on, focus_on, matching, small_abs, small_square;
+    double gan_w, council_w, w01, wtot, wtv;  /* loss weights (0 = term off)                                        */
+    double numel;                             /* mask.numel() of the GLOBAL minibatch                               */
+} cg_gen_loss_hp;
+/* pass 1: scal[G][6] = { sum_scales mean (D(x)-1)^2, sum_scales mean (DC(x)-1)^2, sum 1/(|m-c|+eps), sum m,
+ * sum |dh m|, sum |dw m| } for this rank, and the gradient of the adversarial maps (calc_gen_loss networks.py:84-90,188-194;
+ * focus criteria trainer_council.py:230-250). */
+int cg_gen_loss_fwd(const cg_gen_loss_desc* d, float* scal, void* ws, size_t ws_bytes, void* stream);
+/* pass 2 (scal summed over ranks): assembles the generator loss of every member (trainer_council.py:392-451,497-529,
+ * 559-634), appends to the loss histories and derives w_match (:518-524,576-586), publishes
+ * pub[G][8] = { total of this direction, adv, zero_one, mask_total, TV, council loss, w_match, raw council },
+ * total[g] (+)= direction total, and writes the council-map and mask gradients.  The caller advances head_gan /
+ * head_council by one after a call that appended (gan_on && matching / council_on && matching). */
+int cg_gen_loss_bwd(const cg_gen_loss_desc* d, const cg_gen_loss_hp* hp, const float* scal, double* hist_gan,
+                    double* hist_council, float* total, int accumulate, float* pub, float* d_mask, void* ws,
+                    size_t ws_bytes, void* stream);
+size_t cg_loss_workspace_bytes(int G, int B, int H, int W);
 
 /* ---- optimiser (torch.optim.Adam as used at trainer_council.py:170-179) ----------------------- */
 int cg_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,

@@ -450,9 +450,9 @@ class OracleTrainer:
             o.zero_grad()
         s = {}
         if 'a2b' in self.dirs:  # :740-745, draw order a2b (s_b) then b2a (s_a)
-            s['a2b'] = torch.randn(x_b.size(0), self.style_dim, 1, 1)
+            s['a2b'] = torch.randn(x_b.size(0), self.style_dim, 1, 1).to(x_b.device)
         if 'b2a' in self.dirs:
-            s['b2a'] = torch.randn(x_a.size(0), self.style_dim, 1, 1)
+            s['b2a'] = torch.randn(x_a.size(0), self.style_dim, 1, 1).to(x_a.device)
         self.loss_dis_total_s = []
         self.x_fake_dis = {d: [] for d in self.dirs}
         for i in range(self.N):
@@ -484,9 +484,9 @@ class OracleTrainer:
             o.zero_grad()
         s = {}
         if 'b2a' in self.dirs:  # :806-809, draw order b2a (s_a) then a2b (s_b)
-            s['b2a'] = torch.randn(x_a.size(0), self.style_dim, 1, 1)
+            s['b2a'] = torch.randn(x_a.size(0), self.style_dim, 1, 1).to(x_a.device)
         if 'a2b' in self.dirs:
-            s['a2b'] = torch.randn(x_b.size(0), self.style_dim, 1, 1)
+            s['a2b'] = torch.randn(x_b.size(0), self.style_dim, 1, 1).to(x_b.device)
         less = c['discriminetro_less_style_by']
         fake = {d: [] for d in self.dirs}
         comp = {d: [] for d in self.dirs}
@@ -536,8 +536,8 @@ class OracleTrainer:
         for o in self.gen_opt:
             o.zero_grad()
         # the reference's D / DC parameters also accumulate (never used) grads here; clear them after
-        s_a = torch.randn(x_a.size(0), self.style_dim, 1, 1)  # :284-285 both always drawn, a then b
-        s_b = torch.randn(x_b.size(0), self.style_dim, 1, 1)
+        s_a = torch.randn(x_a.size(0), self.style_dim, 1, 1).to(x_a.device)  # :284-285 both always drawn, a then b
+        s_b = torch.randn(x_b.size(0), self.style_dim, 1, 1).to(x_b.device)
         s = {'a2b': s_b, 'b2a': s_a}
         focus_on = hp['iteration'] > fl['focus_loss_start_at_iter'] and \
             (hp['mask_zero_or_one_w'] != 0 or hp['mask_total_w'] != 0)  # :390

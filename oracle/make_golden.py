@@ -41,6 +41,20 @@ CASES = {
     # BASELINE.json configs[1] at its real resolution (256x256: every layer geometry of the headline workload), council and batch
     # reduced so that the CPU reference and the oracle finish in seconds
     'm2f256_n2_b1': ('male2female', {'council.council_size': 2}, 256, 1, 60001),
+    # ---- round 2: the BASELINE configurations at their real council size, batch and resolution -----------------------------
+    # BASELINE.json configs[1]: male2female 256x256, council_size=4, batch=8 (the configuration the metric is quoted on)
+    'm2f256_n4_b8': ('male2female', {}, 256, 8, 60001),
+    # BASELINE.json configs[2]: selfie2anime 256x256, council_size=4, batch=4 (b2a only, gan_w asymmetry, no focus loss)
+    'anime256_n4_b4': ('selfie2anime', {}, 256, 4, 2001),
+    # BASELINE.json configs[4] per GPU: male2female 512x512, council_size=6, 2 images per GPU
+    'm2f512_n6_b2': ('male2female', {'council.council_size': 6}, 512, 2, 60001),
+    # both directions at once (do_a2b and do_b2a): loss accumulation over directions, two Adam banks per family
+    'glasses64_n2_b2_both': ('glasses', {'council.council_size': 2, 'do_b2a': True}, 64, 2, 20001),
+    # three consecutive iterations with the on/off flip of the council loss live (2 on / 1 off), StepLR decay between them
+    # (step_size 2) and the loss histories evolving: pins every piece of state carried from one iteration to the next
+    'glasses64_n2_b2_iter3': ('glasses', {'council.council_size': 2, 'council.flipOnOff': True,
+                                          'council.flipOnOff_On_iteration': 2, 'council.flipOnOff_Off_iteration': 1,
+                                          'step_size': 2}, 64, 2, 20001, 3),
 }
 
 PROBE_PARAMS = {
@@ -81,8 +95,36 @@ def import_reference():
     return Council_Trainer
 
 
+def _dir_losses(trainer, d):
+    """The loss attributes gen_update publishes for direction d (trainer_council.py:302-322), as floats."""
+    ab = 'ab' if d == 'a2b' else 'ba'
+    return {'loss_gen_adv': [float(v) for v in getattr(trainer, 'loss_gen_adv_%s_s' % d)],
+            'council_loss': [float(v) for v in getattr(trainer, 'council_loss_%s_s' % ab)],
+            'loss_gen_mask_zero_one': [float(v) for v in getattr(trainer, 'loss_gen_mask_zero_one_%s_s' % ab)],
+            'loss_gen_mask_total': [float(v) for v in getattr(trainer, 'loss_gen_mask_total_%s_s' % ab)],
+            'loss_gen_mask_TV': [float(v) for v in getattr(trainer, 'loss_gen_mask_TV_%s_s' % ab)],
+            'w_match': float(getattr(trainer, 'w_match_%s_conf' % d))}
+
+
+def run_iteration(trainer, hp, x_a, x_b, iteration):
+    """One pass of the train.py:241-250 sequence; returns what it published."""
+    hp['iteration'] = iteration
+    rec = {'iteration': iteration}
+    trainer.dis_update(x_a, x_b, hp)
+    rec['loss_dis_total'] = [float(v) for v in trainer.loss_dis_total_s]
+    trainer.loss_dis_council_total_s = None
+    trainer.dis_council_update(x_a, x_b, hp)
+    ran = trainer.loss_dis_council_total_s is not None
+    rec['dis_council_ran'] = ran
+    rec['loss_dis_council_total'] = [float(v) for v in trainer.loss_dis_council_total_s] if ran else []
+    trainer.gen_update(x_a, x_b, hp, iteration)
+    rec['loss_gen_total'] = [float(v) for v in trainer.loss_gen_total_s]
+    return rec
+
+
 def run_case(Council_Trainer, case):
-    cfg, overrides, size, batch, iteration = CASES[case]
+    cfg, overrides, size, batch, iteration = CASES[case][:5]
+    n_iters = CASES[case][5] if len(CASES[case]) > 5 else 1
     hp = load_config(cfg, overrides)
     hp['batch_size'] = batch
     hp['iteration'] = iteration
@@ -102,43 +144,42 @@ def run_case(Council_Trainer, case):
     out = {'case': case, 'config': cfg, 'overrides': overrides, 'size': size, 'batch': batch,
            'iteration': iteration, 'state_seed': 7, 'input_seed': 123, 'rng_seed': hp['random_seed'] + 1,
            'torch': torch.__version__, 'reference': 'Onr/Council-GAN @ 7fe8f8a (unmodified, CPU, shims only)'}
-
-    trainer.dis_update(x_a, x_b, hp)
-    out['loss_dis_total'] = [float(v) for v in trainer.loss_dis_total_s]
-    ran = True
-    trainer.loss_dis_council_total_s = None
-    trainer.dis_council_update(x_a, x_b, hp)
-    ran = trainer.loss_dis_council_total_s is not None
-    out['dis_council_ran'] = ran
-    out['loss_dis_council_total'] = [float(v) for v in trainer.loss_dis_council_total_s] if ran else []
-    trainer.gen_update(x_a, x_b, hp, iteration)
-    out['loss_gen_total'] = [float(v) for v in trainer.loss_gen_total_s]
     d0 = dirs[0]
-    adv = trainer.loss_gen_adv_a2b_s if d0 == 'a2b' else trainer.loss_gen_adv_b2a_s
-    out['loss_gen_adv'] = [float(v) for v in adv]
-    cl = trainer.council_loss_ab_s if d0 == 'a2b' else trainer.council_loss_ba_s
-    out['council_loss'] = [float(v) for v in cl]
-    z1 = trainer.loss_gen_mask_zero_one_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_zero_one_ba_s
-    out['loss_gen_mask_zero_one'] = [float(v) for v in z1]
-    mt = trainer.loss_gen_mask_total_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_total_ba_s
-    out['loss_gen_mask_total'] = [float(v) for v in mt]
-    tv = trainer.loss_gen_mask_TV_ab_s if d0 == 'a2b' else trainer.loss_gen_mask_TV_ba_s
-    out['loss_gen_mask_TV'] = [float(v) for v in tv]
-    out['w_match'] = float(trainer.w_match_a2b_conf if d0 == 'a2b' else trainer.w_match_b2a_conf)
-    # post-iteration parameters (each family stepped exactly once) and the grads that produced them
+    if n_iters > 1:
+        # train.py:225-252,399: same images every iteration here (synthetic), config['iteration'] advances, StepLR steps
+        out['n_iters'] = n_iters
+        out['iters'] = []
+        for k in range(n_iters):
+            rec = run_iteration(trainer, hp, x_a, x_b, iteration + k)
+            rec.update(_dir_losses(trainer, d0))
+            out['iters'].append(rec)
+            trainer.update_learning_rate()
+        out['lr_after'] = {fam: [float(o.param_groups[0]['lr']) for o in getattr(trainer, fam + '_opt_s')]
+                           for fam in ('gen', 'dis', 'dis_council')}
+        out.update(out['iters'][-1])
+        out['iteration'] = iteration
+    else:
+        out.update(run_iteration(trainer, hp, x_a, x_b, iteration))
+        out.update(_dir_losses(trainer, d0))
+    if len(dirs) > 1:
+        out['dirs'] = {d: _dir_losses(trainer, d) for d in dirs}
+        out['dirs']['a2b']['loss_dis'] = [float(v) for v in trainer.loss_dis_a2b_s]
+        out['dirs']['b2a']['loss_dis'] = [float(v) for v in trainer.loss_dis_b2a_s]
+    # post-iteration parameters (each family stepped n_iters times) and the grads of the last step
     post = {}
-    for fam in ('gen', 'dis', 'dis_council'):
-        mods = getattr(trainer, '%s_%s_s' % (fam, d0), None)
-        if mods is None or len(mods) == 0:
-            continue
-        for i in range(N):
-            sd = mods[i].state_dict()
-            named = dict(mods[i].named_parameters())
-            for key in PROBE_PARAMS[fam]:
-                rec = {'post': probe(sd[key])}
-                if fam == 'gen' and named[key].grad is not None:
-                    rec['grad'] = probe(named[key].grad)
-                post['%s.%d.%s' % (fam, i, key)] = rec
+    for d in dirs:
+        for fam in ('gen', 'dis', 'dis_council'):
+            mods = getattr(trainer, '%s_%s_s' % (fam, d), None)
+            if mods is None or len(mods) == 0:
+                continue
+            for i in range(N):
+                sd = mods[i].state_dict()
+                named = dict(mods[i].named_parameters())
+                for key in PROBE_PARAMS[fam]:
+                    rec = {'post': probe(sd[key])}
+                    if fam == 'gen' and named[key].grad is not None:
+                        rec['grad'] = probe(named[key].grad)
+                    post[('%s.%d.%s' % (fam, i, key)) if d == d0 else ('%s_%s.%d.%s' % (fam, d, i, key))] = rec
     out['params'] = post
     # a fresh forward of member 0 AFTER the iteration (pins the updated generator end to end)
     with torch.no_grad():

@@ -33,6 +33,7 @@ class TorchOps:
         self.dtype = dtype
         self.sm_count = 0
         self._launches = 0
+        self._tot64 = {}
 
     def empty(self, *shape):
         return torch.empty(*shape, dtype=self.dtype, device=self.device)
@@ -186,7 +187,8 @@ class TorchOps:
     def acc_slice(self, dst, src, nch):
         dst[..., :nch] += src.reshape(dst.shape[:-1] + (src.shape[-1],))[..., :nch]
 
-    def gather_images(self, pool, idx, x_in, G, Bt):
+    def gather_images(self, pools, idx, x_in, G, Bt):
+        pool = pools if torch.is_tensor(pools) else torch.cat(tuple(pools), 0)
         y = pool[idx.reshape(-1).long()].reshape(G, Bt, *pool.shape[1:])
         if x_in is not None:
             B = x_in.shape[1]
@@ -194,6 +196,9 @@ class TorchOps:
             xi = x_in[0].repeat(reps, 1, 1, 1)[None].expand(G, -1, -1, -1, -1)
             y = torch.cat((y, xi), -1)
         return y.contiguous()
+
+    def stage(self, arrays):
+        return [a.to(self.device) if a.dtype == torch.int32 else a.to(self.device, self.dtype) for a in arrays]
 
     def nchw_to_nhwc(self, x, Cp):
         N, Cc, H, W = x.shape
@@ -242,6 +247,108 @@ class TorchOps:
             tot = (coef[:, 0] * s0 + coef[:, 1] * s1 + coef[:, 2] * s2).sum()
         g, = torch.autograd.grad(tot, m)
         return torch.cat((g, torch.zeros_like(g[..., :1])), -1).contiguous()
+
+    # -- fused losses (same contracts as CudaOps.lsgan_fused / gen_loss_fwd / gen_loss_bwd) -------------------
+    def lsgan_fused(self, outs, nseg, targets, weights, loss_scale, grad_scale, loss_total, accumulate, loss_plain=None,
+                    want_grad=True):
+        G = outs[0].shape[0]
+        t = torch.tensor(targets, dtype=self.dtype, device=self.device)
+        w = torch.tensor(weights, dtype=self.dtype, device=self.device).reshape(G, nseg)
+        tot, plain, douts = 0, 0, []
+        for out in outs:
+            o = out.reshape(G, nseg, -1)
+            n = o.shape[-1]
+            df = o - t[None, :, None]
+            mean = (df ** 2).sum(-1) / n
+            tot = tot + (mean * w).sum(-1)
+            plain = plain + mean.sum(-1)
+            douts.append((grad_scale * w[:, :, None] * 2.0 / n * df).reshape(out.shape).contiguous() if want_grad else None)
+        tot = tot * loss_scale
+        if accumulate:
+            loss_total += tot
+        else:
+            loss_total.copy_(tot)
+        if loss_plain is not None:
+            loss_plain.copy_(plain * loss_scale)
+        return douts
+
+    def gen_loss_fwd(self, adv_outs, cl_outs, mask, center, eps, adv_grad_scale, scal):
+        G = scal.shape[0]
+        scal.zero_()
+        douts = []
+        for out in adv_outs:
+            o = out.reshape(G, -1)
+            scal[:, 0] += ((o - 1) ** 2).sum(-1) / o.shape[-1]
+            douts.append((adv_grad_scale * 2.0 / o.shape[-1] * (o - 1)).reshape(out.shape).contiguous())
+        for out in cl_outs:
+            o = out.reshape(G, -1)
+            scal[:, 1] += ((o - 1) ** 2).sum(-1) / o.shape[-1]
+        if mask is not None:
+            scal[:, 2:] = self.focus_fwd(mask, center, eps)
+        return douts
+
+    def gen_loss_bwd(self, cl_outs, mask, center, eps, scal, hp, hist_gan, hist_council, total, accumulate, pub, want_dmask):
+        """Plain restatement of the device finalisation (csrc/losses.cu gen_loss_bwd_kernel) in float64."""
+        import numpy as np
+        G = total.shape[0]
+        R = hp['hist_size'] + 1
+        sc = scal.detach().double().cpu().numpy()
+        coef = np.zeros((G, 3))
+        cdis = np.zeros(G)
+        for g in range(G):
+            adv, cl = sc[g, 0] / hp['world'], sc[g, 1] / hp['world']
+            l01, msum, ltv = sc[g, 2] / hp['numel'], sc[g, 3] / hp['numel'], (sc[g, 4] + sc[g, 5]) / hp['numel']
+            tot, ltot = 0.0, 0.0
+            if hp['focus_on']:
+                if hp['w01'] != 0:
+                    tot += hp['w01'] * l01
+                    coef[g, 0] = hp['w01'] / hp['numel']
+                if hp['wtv'] != 0:
+                    tot += hp['wtv'] * ltv
+                    coef[g, 2] = hp['wtv'] / hp['numel']
+                if hp['wtot'] != 0:
+                    if hp['small_abs']:
+                        ltot += abs(msum)
+                        coef[g, 1] += hp['wtot'] * np.sign(msum) / hp['numel']
+                    if hp['small_square']:
+                        ltot += msum ** 2
+                        coef[g, 1] += hp['wtot'] * 2.0 * msum / hp['numel']
+                    tot += hp['wtot'] * ltot
+
+            def window(ring, head, drop_first):
+                return [float(ring[g, (head + k) % R]) for k in range(1 if drop_first else 0, hp['hist_size'])]
+            adv32 = float(np.float32(adv)) if self.dtype == torch.float32 else adv
+            if hp['gan_on'] and hp['matching']:
+                mean_gan = (sum(window(hist_gan, hp['head_gan'], True)) + adv32) / hp['hist_size']
+                hist_gan[g, (hp['head_gan'] + hp['hist_size']) % R] = adv32
+            else:
+                mean_gan = sum(window(hist_gan, hp['head_gan'], False)) / hp['hist_size']
+            if hp['gan_on']:
+                tot += hp['gan_w'] * adv
+            w, closs = 1.0, 0.0
+            if hp['council_on']:
+                if hp['matching']:
+                    cl32 = float(np.float32(cl)) if self.dtype == torch.float32 else cl
+                    mean_c = (sum(window(hist_council, hp['head_council'], True)) + cl32) / hp['hist_size']
+                    hist_council[g, (hp['head_council'] + hp['hist_size']) % R] = cl32
+                    w = mean_gan / mean_c
+                w_used = float(np.float32(w)) if self.dtype == torch.float32 else w
+                closs = cl * w_used * hp['council_w']
+                tot += closs
+                cdis[g] = w * hp['council_w']
+            prev = self._tot64[g] if accumulate else 0.0
+            self._tot64[g] = prev + tot
+            total[g] = self._tot64[g]
+            pub[g] = torch.tensor([tot, adv, l01, ltot, ltv, closs, w, cl], dtype=pub.dtype)
+        cl_douts = []
+        for out in cl_outs:
+            o = out.reshape(G, -1)
+            cf = torch.tensor(cdis * 2.0 / (o.shape[-1] * hp['world']), dtype=self.dtype, device=self.device)
+            cl_douts.append((cf[:, None] * (o - 1)).reshape(out.shape).contiguous())
+        d_mask = None
+        if want_dmask:
+            d_mask = self.focus_bwd(mask, torch.tensor(coef, dtype=self.dtype, device=self.device), center, eps)
+        return cl_douts, d_mask
 
     # -- optimiser --------------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

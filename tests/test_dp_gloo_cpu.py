@@ -43,6 +43,7 @@ def _run(gold, x_a, x_b, states, hp):
         torch.randn = saved
     out = {'dis': [float(v) for v in tr.loss_dis_total_s], 'disc': [float(v) for v in tr.loss_dis_council_total_s],
            'gen': [float(v) for v in tr.loss_gen_total_s], 'w_match': float(tr.w_match_a2b_conf)}
+    tr.synchronize()  # the last family's all-reduce + Adam are deferred under data parallelism
     for name, net in tr._nets.items():
         out['p_' + name] = net.bank.data.clone()
     return out
