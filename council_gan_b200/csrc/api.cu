@@ -141,15 +141,20 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     if (!g) return 0;
     ConvDims d = conv_dims(*g);
     size_t need = 0;
-    if (which != 1 && patch_path(*g)) {
+    // the same predicates as the dispatch in cg_conv_fwd / cg_conv_wgrad (the forward's activation is not known here: a tanh
+    // layer falls through to the direct path, so the larger of the two needs is reported)
+    const bool patch_fwd = which == 0 && (g_tc_mode & 1) && patch_path(*g) && g->KH * g->KW >= 16;
+    const bool patch_wgrad = which == 2 && (g_tc_mode & 4) && patch_path(*g);
+    if (patch_fwd || patch_wgrad) {
         cg_conv_geom p = patch_geom(*g);
         ConvDims dp = conv_dims(p);
         size_t inner = which == 2 ? tc_wgrad_ws(p) : 0;
         size_t cs = which == 2 ? colsum_ws(g->G, dp.Mpix, g->Cout) : 0;
         if (cs > inner) inner = cs;
-        return patch_bytes(*g) + 2 * patch_w_bytes(*g) + inner;
+        need = patch_bytes(*g) + 2 * patch_w_bytes(*g) + inner;
+        if (which == 2) return need;
     }
-    if (which == 0 && (g_tc_mode & 1) && tc_fwd_supported(*g)) need = tc_fwd_ws(*g);
+    if (which == 0 && (g_tc_mode & 1) && tc_fwd_supported(*g)) { size_t t = tc_fwd_ws(*g); need = t > need ? t : need; }
     if (which == 1) {
         if (g->ups) need = (size_t)g->G * g->B * d.Hin * d.Win * g->Cin * sizeof(float);
         if ((g_tc_mode & 2) && tc_dgrad_supported(*g)) { size_t t = tc_dgrad_ws(*g); need = t > need ? t : need; }

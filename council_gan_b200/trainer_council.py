@@ -708,14 +708,13 @@ class Council_Trainer(nn.Module):
                 else:
                     dst.copy_(ent[key].detach().to('cpu', dst.dtype).reshape(-1))
             steps.append(int(float(ent['step'])))
-        if steps:
-            for d in self._dirs:
-                self._nets['%s_%s' % (fam, d)].bank.step = max(steps)
+        return max(steps) if steps else None
 
     def resume(self, checkpoint_dir, hyperparameters):
         """Load the latest per-member checkpoints (:898-967); returns the iteration parsed from the file name."""
         self._flush()
         iterations = 0
+        steps = {}  # the flat Adam keeps ONE step count per family (the reference: one per parameter, all equal in practice)
         for i in range(self.council_size):
             for fam in ('gen', 'dis', 'dis_council'):
                 if fam == 'dis_council' and not self.do_dis_council:
@@ -736,10 +735,15 @@ class Council_Trainer(nn.Module):
             try:
                 opt = torch.load(opt_path, map_location='cpu')
                 for fam in ('dis', 'gen') + (('dis_council',) if self.do_dis_council else ()):
-                    self._load_opt_state_dict(fam, i, opt[fam])
+                    st = self._load_opt_state_dict(fam, i, opt[fam])
+                    if st is not None:
+                        steps[fam] = max(steps.get(fam, 0), st)
             except Exception as e:  # the reference warns and carries on as well (:958-959)
                 import warnings
                 warnings.warn('some optimizer FAILED to load (%s: %s): Adam moments restart from zero' % (type(e).__name__, e))
+        for fam, st in steps.items():
+            for d in self._dirs:
+                self._nets['%s_%s' % (fam, d)].bank.step = st
         if iterations > 0:
             print('Resume from iteration %d' % iterations)
             for fam in self._sched_epoch:  # get_scheduler(..., last_epoch=iterations) :953-957

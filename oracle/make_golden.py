@@ -3,7 +3,12 @@
 Runs in the build container only (needs /root/reference, which does not exist on the GPU box).
 Imports the reference read-only with the two out-of-tree shims of SURVEY.md section 8c:
   1. a stub ``torchfile`` module (utils.py:6 imports it; used only by load_vgg16, dead at vgg_w=0);
-  2. ``Tensor.cuda(dev)`` / ``Module.cuda(dev)`` rebound to ``.to(dev)`` so ``cuda_device='cpu'`` works.
+  2. ``Tensor.cuda(dev)`` / ``Module.cuda(dev)`` rebound to ``.to(dev)`` so ``cuda_device='cpu'`` works;
+  3. ``Tensor.cpu()`` returns a COPY, as it does for the CUDA tensors the reference is written for.  Without it the CPU run
+     differs from the CUDA run from the second iteration on: trainer_council.py:578 appends
+     ``dis_council_loss_ab.detach().cpu().numpy()`` to the loss history and :582/:589 then scale that very tensor in place --
+     for a CPU tensor ``.cpu().numpy()`` is a view, so the history would record loss * w_match * council_w instead of the loss.
+     (Single-iteration fixtures are bit-identical with or without this shim: the ratio is taken before the in-place scaling.)
 Loads deterministic synthetic parameters (``council_oracle.synth_all_states``) into the reference's
 ``Council_Trainer``, runs one training iteration (dis_update -> dis_council_update -> gen_update,
 train.py:241-250) and writes the observed values to ``tests/golden/<case>.json``.
@@ -91,6 +96,8 @@ def import_reference():
     import torch.nn as nn
     torch.Tensor.cuda = lambda self, device=None, *a, **k: self.to(device if device is not None else 'cpu')
     nn.Module.cuda = lambda self, device=None: self.to(device if device is not None else 'cpu')
+    _cpu = torch.Tensor.cpu
+    torch.Tensor.cpu = lambda self, *a, **k: _cpu(self, *a, **k).clone() if self.device.type == 'cpu' else _cpu(self, *a, **k)
     from trainer_council import Council_Trainer
     return Council_Trainer
 

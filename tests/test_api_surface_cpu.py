@@ -93,3 +93,109 @@ def test_gating_before_start_iterations():
     tr.dis_council_update(x_a, x_b, hp)  # iteration 100 < 10000
     assert tr.loss_dis_council_total_s == 'untouched'
     assert torch.equal(before, tr._nets['dis_council_a2b'].bank.data)
+
+
+def test_optimizer_file_is_torch_adam_state_dict(tmp_path):
+    """optimizer_{i}.pt holds {'gen','dis','dis_council': torch.optim.Adam.state_dict()} like the reference (:988-992): a real
+    torch.optim.Adam over reference-shaped parameters must load it, moment shapes must be the OIHW parameter shapes, and a
+    reference-written file must round-trip through resume() into our flat moment buffers."""
+    tr, hp, states, x_a, x_b = make()
+    co.seed_all(5)
+    tr.dis_update(x_a, x_b, hp)
+    tr.gen_update(x_a, x_b, hp, hp['iteration'])
+    tr.save(str(tmp_path), 9)
+    opt = torch.load(os.path.join(tmp_path, 'optimizer_1.pt'))
+    assert set(opt) == {'gen', 'dis', 'dis_council'}
+    shapes = {'gen': [s for k, s in co.gen_param_shapes(hp) if not k.endswith('#buf')],
+              'dis': [s for _, s in co.dis_param_shapes(hp, False)], 'dis_council': [s for _, s in co.dis_param_shapes(hp, True)]}
+    for fam in ('gen', 'dis'):
+        params = [torch.zeros(s, requires_grad=True) for s in shapes[fam]]
+        adam = torch.optim.Adam(params, lr=hp['lr'], betas=(hp['beta1'], hp['beta2']), weight_decay=hp['weight_decay'])
+        adam.load_state_dict(opt[fam])  # raises on a layout mismatch
+        st = adam.state_dict()['state']
+        assert len(st) > 0
+        for idx, ent in st.items():
+            assert tuple(ent['exp_avg'].shape) == tuple(shapes[fam][idx]), (fam, idx)
+            assert float(ent['step']) == 1.0
+        if fam == 'gen':  # the style encoder never receives a gradient: no state entries, like the reference
+            n_style = sum(1 for k, _ in co.gen_param_shapes(hp) if k.startswith('enc_style'))
+            assert all(idx >= n_style for idx in st)
+    # a file written by torch.optim.Adam itself (what the reference saves) comes back through resume()
+    params = [torch.randn(s).requires_grad_(True) for s in shapes['dis']]
+    adam = torch.optim.Adam(params, lr=hp['lr'], betas=(hp['beta1'], hp['beta2']), weight_decay=hp['weight_decay'])
+    for p in params:
+        p.grad = torch.randn_like(p)
+    adam.step()
+    adam.step()
+    ref_sd = adam.state_dict()
+    full = torch.load(os.path.join(tmp_path, 'optimizer_0.pt'))
+    full['dis'] = ref_sd
+    torch.save(full, os.path.join(tmp_path, 'optimizer_0.pt'))
+    tr2 = Council_Trainer(hp, 'cpu', _ops=TorchOps('cpu'))
+    tr2.resume(str(tmp_path), hp)
+    assert tr2._nets['dis_a2b'].bank.step == 2
+    back = tr2._opt_state_dict('dis', 0)['state']
+    for idx, ent in ref_sd['state'].items():
+        assert torch.equal(back[idx]['exp_avg'], ent['exp_avg']) and torch.equal(back[idx]['exp_avg_sq'], ent['exp_avg_sq']), idx
+
+
+def test_image_cache_misses_on_a_new_tensor():
+    """The three updates of one iteration share one upload; a NEW host tensor (even with equal contents, even at the address of
+    a freed one) is always uploaded again -- bench.py's e2e leg relies on it."""
+    tr, hp, states, x_a, x_b = make()
+    m0 = tr.img_cache_misses
+    tr._img(x_a)
+    tr._img(x_b)
+    tr._img(x_a)
+    assert tr.img_cache_misses - m0 == 2
+    x_c = x_a.clone()
+    tr._img(x_c)
+    assert tr.img_cache_misses - m0 == 3
+    x_a.add_(1.0)  # in-place change of a cached tensor bumps its version
+    tr._img(x_a)
+    assert tr.img_cache_misses - m0 == 4
+
+
+def test_batched_sample_equals_member_api():
+    """sample() runs all members / images as one stacked pass; row (i * M + j) must equal member j's own encode/decode of image i."""
+    tr, hp, states, x_a, x_b = make()
+    torch.manual_seed(11)
+    out = tr.sample(x_a, x_b, council_member_to_sample_vec=[1, 0])
+    torch.manual_seed(11)
+    s2 = torch.randn(x_a.size(0), hp['gen']['style_dim'], 1, 1)
+    row = 0
+    for i in range(x_a.size(0)):
+        xi = x_a[i:i + 1]
+        for j in (1, 0):
+            g = tr.gen_a2b_s[j]
+            c, _ = g.encode(xi)
+            o1, m1 = g.decode(c, tr.s_b[i:i + 1], xi, return_mask=True)
+            o2 = g.decode(c, s2[i:i + 1], xi)
+            # batch-1 and stacked convolutions sum in different orders on CPU; the mask head is tanh(10 h): fp32 noise x10
+            assert torch.allclose(out[0][row], xi[0]) and (out[1][row] - m1[0]).abs().max() < 2e-3
+            assert (out[2][row] - o1[0]).abs().max() < 2e-3 and (out[3][row] - o2[0]).abs().max() < 2e-3
+            row += 1
+    rec = tr.sample(x_a, x_b, return_mask=False)  # second entry = reconstruction with each member's own style code
+    c, s_fake = tr.gen_a2b_s[1].encode(x_a[0:1])
+    assert (rec[1][1] - tr.gen_a2b_s[1].decode(c, s_fake, x_a[0:1])[0]).abs().max() < 2e-3
+
+
+def test_weight_init_statistics():
+    """weights_init (utils.py:402-422): kaiming fan_in normal for generators, N(0, 0.02) for both discriminators, zero biases."""
+    import math
+    tr, hp, states, x_a, x_b = make()
+    co.seed_all(1)
+    tr2 = Council_Trainer(hp, 'cpu', _ops=TorchOps('cpu'))
+    sd = tr2.gen_a2b_s[0].state_dict()
+    w = sd['enc_content.model.3.model.0.model.0.conv.weight']  # 256 x 256 x 3 x 3
+    assert abs(w.std().item() / math.sqrt(2.0 / (w.shape[1] * 9)) - 1) < 0.02 and abs(w.mean().item()) < 1e-3
+    w = sd['mlp.model.1.fc.weight']
+    assert abs(w.std().item() / math.sqrt(2.0 / w.shape[1]) - 1) < 0.03
+    assert all(float(v.abs().max()) == 0 for k, v in sd.items() if k.endswith('.bias'))
+    for net in (tr2.dis_a2b_s[1], tr2.dis_council_a2b_s[0]):
+        sdd = net.state_dict()
+        w = sdd['cnns.0.2.conv.weight']
+        assert abs(w.std().item() / 0.02 - 1) < 0.02 and abs(w.mean().item()) < 2e-4
+        assert all(float(v.abs().max()) == 0 for k, v in sdd.items() if k.endswith('.bias'))
+    a, b = tr2.gen_a2b_s[0].state_dict(), tr2.gen_a2b_s[1].state_dict()
+    assert not torch.equal(a['dec.model.2.conv.weight'], b['dec.model.2.conv.weight'])  # members are initialised independently

@@ -83,3 +83,33 @@ def test_two_ranks_equal_one_rank_global_batch():
         if k.startswith('p_'):
             diff = (v - ret[k]).abs().max().item()
             assert diff < 1e-7, (k, diff)  # << lr = 1e-4: same update up to fp64 summation order
+
+
+def _init_worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from council_gan_b200.trainer_council import Council_Trainer
+    from ops_torch import TorchOps
+    gold = load_golden(CASE)
+    hp, states, x_a, x_b = setup_case(gold)
+    co.seed_all(100 + rank)  # ranks seeded DIFFERENTLY (seed + rank is common practice)
+    tr = Council_Trainer(hp, 'cpu', _ops=TorchOps('cpu'))
+    sums = torch.tensor([float(net.bank.data.double().sum()) for net in tr._nets.values()] +
+                        [float(tr._nets['gen_a2b'].frozen.data.double().sum())], dtype=torch.float64)
+    got = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(got, sums)
+    if rank == 0:
+        ret['equal'] = bool(torch.equal(got[0], got[1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_ranks_seeded_differently_start_from_rank0_parameters():
+    """Only gradients are all-reduced during training, so the constructor broadcasts rank 0's parameter banks."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_init_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert dict(ret)['equal'] is True

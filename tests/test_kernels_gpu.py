@@ -241,6 +241,17 @@ def test_image_helpers(ops, ref):
         got = ops.gather_images(pool, idx, xi, 2, 6)
         want = ref.gather_images(d(pool), idx, d(xi), 2, 6)
         assert torch.equal(got.double(), want)
+    # two pools without torch.cat: slots < 3 read pool_a, the rest pool_b
+    pool_a, pool_b = pool[:3].contiguous(), pool[3:].contiguous()
+    for xi in (None, x_in):
+        got = ops.gather_images((pool_a, pool_b), idx, xi, 2, 6)
+        assert torch.equal(got.double(), ref.gather_images(d(pool), idx, d(xi), 2, 6))
+    # host -> device staging: one pinned buffer, views keep dtype / shape / contents
+    a, b = torch.randn(1, 3, 1, 1, 64), torch.arange(24, dtype=torch.int32).reshape(2, 12)
+    for _ in range(10):  # more rounds than ring slots: buffers are reused safely
+        da, db = ops.stage([a, b])
+        assert da.is_cuda and da.dtype == torch.float32 and db.dtype == torch.int32
+        assert torch.equal(da.cpu(), a) and torch.equal(db.cpu(), b)
     img = rnd(3, 3, H, W, seed=8)
     nhwc = ops.nchw_to_nhwc(img, 4)
     assert torch.equal(nhwc.double(), ref.nchw_to_nhwc(d(img), 4))
@@ -268,6 +279,69 @@ def test_losses(ops, ref):
     check(ops.focus_bwd(mask, fc, 0.5, 0.01), ref.focus_bwd(d(mask), d(fc), 0.5, 0.01), 5e-5, 'focus bwd')
     fc[:, 2] = 0  # TV off (male2female config)
     check(ops.focus_bwd(mask, fc, 0.5, 0.01), ref.focus_bwd(d(mask), d(fc), 0.5, 0.01), 5e-5, 'focus bwd no tv')
+
+
+def test_fused_losses(ops, ref):
+    """cg_lsgan_fused / cg_gen_loss_fwd / cg_gen_loss_bwd (csrc/losses.cu) against their plain restatement in float64:
+    loss values, every gradient, the published values and the history rings, over the gating combinations."""
+    G, B = 3, 2
+    outs = [rnd(G, 3 * B, 5, 4, 1, seed=1), rnd(G, 3 * B, 3, 2, 1, seed=2)]
+    wrows = [[2.0, 0.5, 0.5], [1.0, 1.0, 0.25], [0.5, 2.0, 3.0]]
+    tot, plain = torch.full((G,), 3.0, device=DEV), torch.zeros(G, device=DEV)
+    rtot, rplain = tot.double().clone(), plain.double().clone()
+    for acc in (False, True):
+        douts = ops.lsgan_fused(outs, 3, [0.0, 1.0, 1.0], wrows, 0.5, 0.25, tot, acc, plain)
+        rd = ref.lsgan_fused([d(o) for o in outs], 3, [0.0, 1.0, 1.0], wrows, 0.5, 0.25, rtot, acc, rplain)
+        check(tot, rtot, 2e-5, 'lsgan_fused total acc=%s' % acc)
+        check(plain, rplain, 2e-5, 'lsgan_fused plain')
+        for a, b in zip(douts, rd):
+            check(a, b, 2e-5, 'lsgan_fused grad')
+    mask = torch.sigmoid(rnd(G, B, 11, 9, 4, seed=3, scale=3.0))
+    mask[..., 3] = 0
+    adv = [rnd(G, B, 4, 4, 1, seed=4), rnd(G, B, 2, 2, 1, seed=5)]
+    cl = [rnd(G, B, 6, 6, 1, seed=6), rnd(G, B, 3, 3, 1, seed=7)]
+    hist = 5
+    combos = [dict(gan_on=1, council_on=1, focus_on=1, matching=1, small_abs=0, small_square=1, wtv=0.0),
+              dict(gan_on=1, council_on=1, focus_on=1, matching=1, small_abs=1, small_square=1, wtv=2.2),
+              dict(gan_on=1, council_on=0, focus_on=0, matching=1, small_abs=0, small_square=1, wtv=0.0),
+              dict(gan_on=1, council_on=1, focus_on=0, matching=0, small_abs=0, small_square=1, wtv=0.0),
+              dict(gan_on=0, council_on=1, focus_on=1, matching=1, small_abs=0, small_square=1, wtv=0.0)]
+    for ci, c in enumerate(combos):
+        a_in = adv if c['gan_on'] else []
+        c_in = cl if c['council_on'] else []
+        m_in = mask if c['focus_on'] else None
+        scal, rscal = ops.empty(G, 6), torch.zeros(G, 6, dtype=torch.float64, device=DEV)
+        d_adv = ops.gen_loss_fwd(a_in, c_in, m_in, 0.5, 0.01, 24.0 / 2, scal)
+        r_adv = ref.gen_loss_fwd([d(o) for o in a_in], [d(o) for o in c_in], d(m_in), 0.5, 0.01, 24.0 / 2, rscal)
+        check(scal, rscal, 5e-5, 'gen_loss_fwd scal combo %d' % ci)
+        for a, b in zip(d_adv, r_adv):
+            check(a, b, 2e-5, 'adv grad')
+        hg = (torch.rand(G, hist + 1, dtype=torch.float64) + 0.5).to(DEV)
+        hc = (torch.rand(G, hist + 1, dtype=torch.float64) + 0.5).to(DEV)
+        rhg, rhc = hg.clone(), hc.clone()
+        hp = dict(world=2, hist_size=hist, head_gan=4, head_council=2, gan_w=24.0, council_w=4.0, w01=0.5, wtot=57.0,
+                  numel=float(2 * B * 3 * 11 * 9), **c)
+        for acc in (False, True):  # accumulate: the second direction adds to the double-precision total kept by the first call
+            total, pub = torch.full((G,), 9.0, device=DEV), ops.empty(G, 8)
+            rtotal, rpub = total.double().clone(), torch.zeros(G, 8, dtype=torch.float64, device=DEV)
+            d_cl, d_mask = ops.gen_loss_bwd(c_in, m_in, 0.5, 0.01, scal, hp, hg, hc, total, acc, pub, c['focus_on'] == 1)
+            r_cl, r_mask = ref.gen_loss_bwd([d(o) for o in c_in], d(m_in), 0.5, 0.01, scal.double(), hp, rhg, rhc, rtotal, acc, rpub,
+                                            c['focus_on'] == 1)
+            check(total, rtotal, 2e-6, 'total combo %d acc %s' % (ci, acc))
+            check(pub, rpub, 2e-6, 'published values combo %d' % ci)
+            for a, b in zip(d_cl, r_cl):
+                check(a, b, 2e-5, 'council map grad')
+            if c['focus_on']:
+                check(d_mask, r_mask, 5e-5, 'mask grad combo %d' % ci)
+            else:
+                assert d_mask is None
+            # the kernel stores the float32-rounded loss (like the reference's history); the float64 restatement does not round
+            assert torch.allclose(hg, rhg, rtol=0, atol=1e-6) and torch.allclose(hc, rhc, rtol=0, atol=1e-6), 'history rings'
+    # the scratch buffer is left clean: a second identical call gives identical results
+    t1, t2 = ops.empty(G), ops.empty(G)
+    ops.lsgan_fused(outs, 3, [0.0, 1.0, 1.0], wrows, 1.0, 1.0, t1, False)
+    ops.lsgan_fused(outs, 3, [0.0, 1.0, 1.0], wrows, 1.0, 1.0, t2, False)
+    assert torch.equal(t1, t2)
 
 
 def test_adam(ops, ref):
@@ -304,3 +378,59 @@ def test_full_size_adjoint_identities(ops):
     zm = z.double().mean(dim=(2, 3))
     zv = z.double().var(dim=(2, 3), unbiased=False)
     assert zm.abs().max().item() < 1e-4 and (zv - 1).abs().max().item() < 1e-3
+
+
+# ---- every distinct production geometry of BASELINE configs[1] (male2female 256x256, council 4, batch 8; the council
+# discriminator sees (1+U)*B = 32 images per member) against the float64 reference of the same convolution ----------------
+PROD_CASES = [
+    # name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups, check dgrad/wgrad
+    ('prod_e0_7x7_img', 4, 1, 8, 256, 256, 4, 64, 7, 1, 3, False, True),
+    ('prod_e1_4x4s2_64_128', 4, 4, 8, 256, 256, 64, 128, 4, 2, 1, False, True),
+    ('prod_e2_4x4s2_128_256', 4, 4, 8, 128, 128, 128, 256, 4, 2, 1, False, True),
+    ('prod_res_3x3_256', 4, 4, 8, 64, 64, 256, 256, 3, 1, 1, False, True),
+    ('prod_u1_3x3_256_128_folded_ups', 4, 4, 8, 64, 64, 256, 128, 3, 1, 1, True, False),
+    ('prod_u1_3x3_256_128', 4, 4, 8, 128, 128, 256, 128, 3, 1, 1, False, True),
+    ('prod_u2_3x3_128_128', 4, 4, 8, 128, 128, 128, 128, 3, 1, 1, False, True),
+    ('prod_u3_3x3_128_64_folded_ups', 4, 4, 8, 128, 128, 128, 64, 3, 1, 1, True, False),
+    ('prod_u3_3x3_128_64', 4, 4, 8, 256, 256, 128, 64, 3, 1, 1, False, True),
+    ('prod_u4_3x3_64_64', 4, 4, 8, 256, 256, 64, 64, 3, 1, 1, False, True),
+    ('prod_h_1x1_64_64', 4, 4, 8, 256, 256, 64, 64, 1, 1, 0, False, True),
+    ('prod_h3_1x1_64_12', 4, 4, 8, 256, 256, 64, 12, 1, 1, 0, False, True),
+    ('prod_d0_4x4s2_img_b16', 4, 4, 16, 256, 256, 4, 64, 4, 2, 1, False, True),
+    ('prod_d3_4x4s2_256_512_b16', 4, 4, 16, 32, 32, 256, 512, 4, 2, 1, False, True),
+    ('prod_dc0_3x3_pair_b32', 4, 4, 32, 256, 256, 8, 64, 3, 1, 1, False, True),
+    ('prod_dc1_4x4s2_64_128_b32', 4, 4, 32, 256, 256, 64, 128, 4, 2, 1, False, True),
+    ('prod_dc2_4x4s2_128_256_b32', 4, 4, 32, 128, 128, 128, 256, 4, 2, 1, False, True),
+    ('prod_dc3_4x4s2_256_512_b32', 4, 4, 32, 64, 64, 256, 512, 4, 2, 1, False, True),
+    ('prod_dc4_1x1_512_512_b32', 4, 4, 32, 32, 32, 512, 512, 1, 1, 0, False, True),
+]
+
+
+@pytest.mark.parametrize('case', PROD_CASES, ids=[c[0] for c in PROD_CASES])
+def test_production_geometry_vs_fp64(ops, ref, case):
+    """Forward, data gradient and weight gradient of the default (tensor-core) dispatch at the exact shapes the bench runs,
+    against float64 torch, at the TF32 tolerance (4e-3 of the tensor's magnitude)."""
+    name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups, bwd = case
+    tol = 4e-3
+    x = rnd(Gx, B, H, W, Cin, seed=21)
+    w = rnd(G, Cout, K, K, Cin, seed=22, scale=1.0 / (K * K * Cin) ** 0.5)
+    y = ops.conv_fwd(x, w, None, stride, pad, ups=ups)
+    dy = rnd(*y.shape, seed=23) if bwd else None
+    xs = (G, B, H, W, Cin)
+    dx = ops.conv_dgrad(dy, w, xs, stride, pad) if bwd else None
+    dw = torch.empty_like(w)
+    if bwd:
+        ops.conv_wgrad(x, dy, dw, None, stride, pad)
+    # float64 reference one member at a time (memory)
+    for g in range(G):
+        xg = d(x[g if Gx > 1 else 0:(g if Gx > 1 else 0) + 1])
+        wg = d(w[g:g + 1])
+        check(y[g:g + 1], ref.conv_fwd(xg, wg, None, stride, pad, ups=ups), tol, '%s fwd member %d' % (name, g))
+        if bwd:
+            dyg = d(dy[g:g + 1])
+            check(dx[g:g + 1], ref.conv_dgrad(dyg, wg, (1, B, H, W, Cin), stride, pad), tol, '%s dgrad member %d' % (name, g))
+            rw = torch.zeros_like(wg)
+            ref.conv_wgrad(xg, dyg, rw, None, stride, pad)
+            check(dw[g:g + 1], rw, tol, '%s wgrad member %d' % (name, g))
+        del xg, wg
+        torch.cuda.empty_cache()
