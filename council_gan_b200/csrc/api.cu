@@ -137,6 +137,15 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
 
 extern "C" uint64_t cg_launch_count(void) { return g_launches.load(); }
 
+extern "C" int cg_zero(void* ptr, size_t bytes, void* stream) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("cg_zero: %s", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
 extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     if (!g) return 0;
     ConvDims d = conv_dims(*g);

@@ -80,6 +80,7 @@ _SIGS = {
     'cg_gen_loss_fwd': (C.c_int, [C.POINTER(GenLossDesc), _fp, _fp, C.c_size_t, _fp]),
     'cg_gen_loss_bwd': (C.c_int, [C.POINTER(GenLossDesc), C.POINTER(GenLossHp), _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     'cg_loss_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'cg_zero': (C.c_int, [_fp, C.c_size_t, _fp]),
     'cg_adam_step': (C.c_int, [_fp, _fp, _fp, _fp, C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, _fp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -127,7 +128,7 @@ class CudaOps:
             raise RuntimeError('libcouncil_b200.so is built for sm_100a only; device is sm_%d%d' % self.cc)
         self._ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
         # dedicated, zero-initialised scratch of the fused loss kernels (ticket counter + partial sums); grown on demand
-        self._loss_ws = torch.zeros(1 << 16, dtype=torch.uint8, device=self.device)
+        self._loss_ws = self._zero_bytes(1 << 16)
         # small per-step host data (style noise, peer index tables): ONE pinned staging buffer and ONE async H2D copy per
         # update instead of a pageable `torch.tensor(...).to(device)` (a hidden host sync) per table
         self._stage_ring = [None] * 8
@@ -153,8 +154,15 @@ class CudaOps:
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
+    def _zero_bytes(self, n):
+        t = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cg_zero(t.data_ptr(), n, self._stream()), 'cg_zero')
+        return t
+
     def zeros(self, *shape):
-        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        t = torch.empty(*shape, dtype=torch.float32, device=self.device)
+        self._ck(self.lib.cg_zero(t.data_ptr(), t.numel() * 4, self._stream()), 'cg_zero')
+        return t
 
     def launch_count(self):
         return int(self.lib.cg_launch_count())
@@ -451,7 +459,7 @@ class CudaOps:
     def _loss_scratch(self, G, B=0, H=0, W=0):
         need = int(self.lib.cg_loss_workspace_bytes(G, B, H, W))
         if need > self._loss_ws.numel():
-            self._loss_ws = torch.zeros(need + 4096, dtype=torch.uint8, device=self.device)
+            self._loss_ws = self._zero_bytes(need + 4096)
         return self._loss_ws
 
     def lsgan_fused(self, outs, nseg, targets, weights, loss_scale, grad_scale, loss_total, accumulate, loss_plain=None,

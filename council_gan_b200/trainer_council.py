@@ -108,8 +108,8 @@ class Council_Trainer(nn.Module):
         object.__setattr__(self, 'ops', _ops)
         # loss histories of the matching (:81-92, deque(np.ones(hist))): float64 rings [N][hist+1] on the device, window start
         # kept on the host; exported as deques by the los_hist_{gan,council}_{a2b,b2a}_s attributes
-        rings = {d: {'gan': torch.ones(N, hist + 1, dtype=torch.float64, device=_ops.device),
-                     'council': torch.ones(N, hist + 1, dtype=torch.float64, device=_ops.device),
+        rings = {d: {'gan': torch.ones(N, hist + 1, dtype=torch.float64).to(_ops.device),
+                     'council': torch.ones(N, hist + 1, dtype=torch.float64).to(_ops.device),
                      'head_gan': 0, 'head_council': 0} for d in self._dirs}
         object.__setattr__(self, '_rings', rings)
         dist = _dist()
@@ -217,7 +217,6 @@ class Council_Trainer(nn.Module):
                 ref = torch.randn(net.G, spec.cout, spec.cin, spec.k, spec.k) * std
                 for i in range(net.G):
                     spec.import_weight(w[i], ref[i])
-                b.p(spec.bname).zero_()
 
     # nn.Module surface the reference's callers touch
     def cuda(self, device=None):

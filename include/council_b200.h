@@ -202,6 +202,9 @@ int cg_gen_loss_bwd(const cg_gen_loss_desc* d, const cg_gen_loss_hp* hp, const f
                     size_t ws_bytes, void* stream);
 size_t cg_loss_workspace_bytes(int G, int B, int H, int W);
 
+/* plumbing: p[0:bytes] = 0 on `stream` (cudaMemsetAsync; keeps framework fill kernels out of the launch list) */
+int cg_zero(void* p, size_t bytes, void* stream);
+
 /* ---- optimiser (torch.optim.Adam as used at trainer_council.py:170-179) ----------------------- */
 int cg_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);

@@ -211,7 +211,9 @@ def test_baseline_configuration_vs_reference_golden(case):
                     worst = max(worst, abs(a - b))
                     assert abs(a - b) <= 2.1 * lr + 1e-6, (fam, i, key, a, b)
                 assert abs(got['absmean'] - rec['post']['absmean']) <= 1.0 * lr + 1e-4 * abs(rec['post']['absmean']), (fam, i, key)
-                if fam == 'gen' and 'grad' in rec and key in ('dec.model.9.conv.weight', 'dec.model.9.conv.bias'):
+                # gradient norm of the head layer: only without focus loss -- sign(m-.5)/(|m-.5|+eps)^2 on masks near 0.5 makes the
+                # gradient discontinuous in the mask (TF32 vs fp32 pixels flip sides; profiles/r01_grad_noise.log)
+                if fam == 'gen' and 'grad' in rec and not gold['loss_gen_mask_zero_one'] and key in ('dec.model.9.conv.weight', 'dec.model.9.conv.bias'):
                     g = tr._nets['gen_' + d0]
                     spec = [s for s in g._specs() if key in (s.wname, s.bname)][0]
                     gg = g.bank.g(key)[i]
