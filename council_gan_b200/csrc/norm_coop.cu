@@ -1,0 +1,403 @@
+// Single-launch instance norm / AdaIN: statistics + normalise (+activation, +residual, +x2 upsample) in ONE kernel, and
+// its backward (both reductions + apply) in ONE kernel, with the second pass over the tensor served from L2.
+//
+// Why: the two-kernel forms (in_stats + norm_act_fwd, norm_bwd_partial/final/apply in norm.cu) are HBM-bound and read the
+// convolution output y twice from HBM (three reads of (y, dz) + ... in the backward); at 256x256 the tensors are several
+// hundred MB, far beyond the 126 MB L2, so nothing survives between the passes.  Here a launch works on only `conc`
+// instances (one instance = one image of one council member: the unit instance norm reduces over, networks.py:483,640-653)
+// at a time, sized so that conc * bytes(instance) fits comfortably in L2, and all `cpi` CTAs that share an instance run
+// its reduction pass, meet at a per-instance barrier, and immediately re-read the same pixels -- now L2 hits -- for the
+// apply pass.  HBM traffic: forward 1 read + 1 write (was 2 + 1), backward 2 reads + 1 write (was 4 + 1).
+//
+// Layout: persistent grid of conc * cpi CTAs, all co-resident (grid <= SMs x resident CTAs per SM, checked at launch);
+// CTA (s, j) owns pixel slice j of the instance in slot s of every round.  Barrier: one monotonically increasing counter
+// per slot (zeroed by the host-side memset node of the same call), arrival = release-add, wait = acquire-spin.  Partial sums
+// are double-buffered by round parity (a CTA can only be one round ahead of its group).
+#include "common.cuh"
+#include <cstdlib>
+
+namespace cg {
+
+constexpr int NC_THREADS = 512;
+constexpr int NC_U = 4;   // rows in flight per thread (apply passes, backward reduction: two tensors)
+constexpr int NC_U1 = 8;  // rows in flight per thread in the forward reduction pass (one tensor, HBM latency): 64 KB per SM
+
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        volatile unsigned int* vc = counter;
+        while (*vc < target) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct CoopP {
+    const float* y; const float* adain; const float* res; const float* dz;
+    const float* mean_in; const float* rstd_in;
+    float* z; float* dy; float* d_adain; float* mean_out; float* rstd_out;
+    float* part;              // [2 parities][conc][cpi][C][2]
+    unsigned int* counters;   // [conc]
+    int NI, conc, cpi, P, off, H, W, C, act, ups;
+    float eps;
+};
+
+struct Lanes {
+    int lanes, rowl, lane, rl;
+    __device__ Lanes(int C) {
+        lanes = C >> 2;
+        rowl = NC_THREADS / lanes;
+        lane = threadIdx.x % lanes;
+        rl = threadIdx.x / lanes;
+    }
+};
+
+// cross-row reduction of per-thread (s, q) float4 pairs; result valid in threads with rl == 0
+__device__ __forceinline__ void fold_rows(const Lanes& lm, float4& s, float4& q, float4 (*sm)[NC_THREADS]) {
+    sm[0][threadIdx.x] = s;
+    sm[1][threadIdx.x] = q;
+    __syncthreads();
+    if (lm.rl == 0) {
+        for (int k = 1; k < lm.rowl; k++) {
+            float4 a = sm[0][k * lm.lanes + lm.lane], b = sm[1][k * lm.lanes + lm.lane];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+        }
+    }
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NC_THREADS, 1) norm_coop_fwd_kernel(const CoopP p) {
+    __shared__ float4 sm[2][NC_THREADS];
+    __shared__ float s_a[256], s_b[256];
+    const int slot = blockIdx.x / p.cpi, j = blockIdx.x - slot * p.cpi;
+    const int HW = p.H * p.W, C = p.C;
+    Lanes lm(C);
+    const int c = lm.lane * 4;
+    const int r0 = (int)((long)HW * j / p.cpi), r1 = (int)((long)HW * (j + 1) / p.cpi);
+    const int rounds = (p.NI + p.conc - 1) / p.conc;
+    for (int rd = 0; rd < rounds; rd++) {
+        const int gb = rd * p.conc + slot;
+        if (gb >= p.NI) break;
+        // ---- pass 1: partial sum / sum of squares of this CTA's pixel slice (HBM read)
+        const float* yb = p.y + (long)gb * HW * C + c;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        for (int r = r0 + lm.rl; r < r1; r += NC_U1 * lm.rowl) {
+            float4 v[NC_U1];
+#pragma unroll
+            for (int u = 0; u < NC_U1; u++) {
+                const int rr = r + u * lm.rowl;
+                v[u] = rr < r1 ? ld_cg4(yb + (long)rr * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < NC_U1; u++) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q.x += v[u].x * v[u].x; q.y += v[u].y * v[u].y; q.z += v[u].z * v[u].z; q.w += v[u].w * v[u].w;
+            }
+        }
+        fold_rows(lm, s, q, sm);
+        float* pbuf = p.part + ((long)((rd & 1) * p.conc + slot) * p.cpi) * C * 2;
+        if (lm.rl == 0) {
+            float* o = pbuf + ((long)j * C + c) * 2;
+            *reinterpret_cast<float4*>(o) = make_float4(s.x, q.x, s.y, q.y);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(s.z, q.z, s.w, q.w);
+        }
+        group_barrier(p.counters + slot, (unsigned int)(p.cpi * (rd + 1)));
+        // ---- finalise: every CTA of the group folds the cpi partials (fp64) into mean / rstd and the affine coefficients
+        for (int ch = threadIdx.x; ch < C; ch += NC_THREADS) {
+            double ss = 0.0, qq = 0.0;
+            for (int k = 0; k < p.cpi; k++) {
+                float2 v = __ldcg(reinterpret_cast<const float2*>(pbuf + ((long)k * C + ch) * 2));
+                ss += (double)v.x;
+                qq += (double)v.y;
+            }
+            double m = ss / HW;
+            double var = qq / HW - m * m;
+            if (var < 0.0) var = 0.0;
+            const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+            float ga = 1.f, be = 0.f;
+            if (p.adain) {
+                const float* ap = p.adain + (long)gb * p.P + p.off;
+                be = __ldg(ap + ch);
+                ga = __ldg(ap + C + ch);
+            }
+            const float a = ga * rstd;
+            s_a[ch] = a;
+            s_b[ch] = be - mean * a;
+            if (j == 0) {
+                p.mean_out[(long)gb * C + ch] = mean;
+                p.rstd_out[(long)gb * C + ch] = rstd;
+            }
+        }
+        __syncthreads();
+        const float4 a = *reinterpret_cast<const float4*>(s_a + c), b = *reinterpret_cast<const float4*>(s_b + c);
+        // ---- pass 2: normalise the same slice (L2 hits), activation, residual, optional x2 nearest upsample
+        const float* rb = p.res ? p.res + (long)gb * HW * C + c : nullptr;
+        for (int r = r0 + lm.rl; r < r1; r += NC_U * lm.rowl) {
+            float4 v[NC_U], e[NC_U];
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr < r1) {
+                    v[u] = ld_cg4(yb + (long)rr * C);
+                    if (rb) e[u] = ld_cg4(rb + (long)rr * C);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr >= r1) break;
+                float4 o;
+                o.x = fmaf(v[u].x, a.x, b.x); o.y = fmaf(v[u].y, a.y, b.y); o.z = fmaf(v[u].z, a.z, b.z); o.w = fmaf(v[u].w, a.w, b.w);
+                if (p.act == CG_ACT_RELU) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (rb) {
+                    o.x += e[u].x; o.y += e[u].y; o.z += e[u].z; o.w += e[u].w;
+                }
+                if (!p.ups) {
+                    *reinterpret_cast<float4*>(p.z + ((long)gb * HW + rr) * C + c) = o;
+                } else {
+                    int h = rr / p.W, w = rr - h * p.W;
+                    long W2 = 2L * p.W;
+                    float* zp = p.z + (((long)gb * 2 * p.H + 2 * h) * W2 + 2 * w) * C + c;
+                    *reinterpret_cast<float4*>(zp) = o;
+                    *reinterpret_cast<float4*>(zp + C) = o;
+                    *reinterpret_cast<float4*>(zp + W2 * C) = o;
+                    *reinterpret_cast<float4*>(zp + W2 * C + C) = o;
+                }
+            }
+        }
+        __syncthreads();  // s_a / s_b / sm are reused by the next round
+    }
+}
+
+// ---- backward --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 coop_load_dz(const CoopP& p, int gb, int r, int c) {
+    if (!p.ups) return ld_cg4(p.dz + ((long)gb * p.H * p.W + r) * p.C + c);
+    int h = r / p.W, w = r - h * p.W;
+    long W2 = 2L * p.W;
+    const float* zp = p.dz + (((long)gb * 2 * p.H + 2 * h) * W2 + 2 * w) * p.C + c;
+    float4 a = ld_cg4(zp), b = ld_cg4(zp + p.C), cc = ld_cg4(zp + W2 * p.C), d = ld_cg4(zp + W2 * p.C + p.C);
+    return make_float4(a.x + b.x + cc.x + d.x, a.y + b.y + cc.y + d.y, a.z + b.z + cc.z + d.z, a.w + b.w + cc.w + d.w);
+}
+
+__global__ void __launch_bounds__(NC_THREADS, 1) norm_coop_bwd_kernel(const CoopP p) {
+    __shared__ float4 sm[2][NC_THREADS];
+    __shared__ float s_m1[256], s_m2[256];
+    const int slot = blockIdx.x / p.cpi, j = blockIdx.x - slot * p.cpi;
+    const int HW = p.H * p.W, C = p.C;
+    Lanes lm(C);
+    const int c = lm.lane * 4;
+    const int r0 = (int)((long)HW * j / p.cpi), r1 = (int)((long)HW * (j + 1) / p.cpi);
+    const int rounds = (p.NI + p.conc - 1) / p.conc;
+    for (int rd = 0; rd < rounds; rd++) {
+        const int gb = rd * p.conc + slot;
+        if (gb >= p.NI) break;
+        // affine of the forward pass: pre-activation = a*y + b (ReLU mask), xhat = (y - mu) * rs
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mean_in + (long)gb * C + c));
+        const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rstd_in + (long)gb * C + c));
+        float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.adain) {
+            const float* ap = p.adain + (long)gb * p.P + p.off;
+            be = __ldg(reinterpret_cast<const float4*>(ap + c));
+            ga = __ldg(reinterpret_cast<const float4*>(ap + C + c));
+        }
+        const float4 a = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+        const float4 b = make_float4(be.x - mu.x * a.x, be.y - mu.y * a.y, be.z - mu.z * a.z, be.w - mu.w * a.w);
+        const float* yb = p.y + (long)gb * HW * C + c;
+        // ---- pass 1: sum g1, sum g1 * xhat  (g1 = dz * act'(pre)); HBM reads of y and dz
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        for (int r = r0 + lm.rl; r < r1; r += NC_U * lm.rowl) {
+            float4 vv[NC_U], gg[NC_U];
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr < r1) {
+                    vv[u] = ld_cg4(yb + (long)rr * C);
+                    gg[u] = coop_load_dz(p, gb, rr, c);
+                } else {
+                    vv[u] = mu;
+                    gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                float4 v = vv[u], g1 = gg[u];
+                if (p.act == CG_ACT_RELU) {
+                    if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
+                    if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
+                    if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
+                    if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+                }
+                s.x += g1.x; s.y += g1.y; s.z += g1.z; s.w += g1.w;
+                q.x += g1.x * (v.x - mu.x) * rs.x; q.y += g1.y * (v.y - mu.y) * rs.y;
+                q.z += g1.z * (v.z - mu.z) * rs.z; q.w += g1.w * (v.w - mu.w) * rs.w;
+            }
+        }
+        fold_rows(lm, s, q, sm);
+        float* pbuf = p.part + ((long)((rd & 1) * p.conc + slot) * p.cpi) * C * 2;
+        if (lm.rl == 0) {
+            float* o = pbuf + ((long)j * C + c) * 2;
+            *reinterpret_cast<float4*>(o) = make_float4(s.x, q.x, s.y, q.y);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(s.z, q.z, s.w, q.w);
+        }
+        group_barrier(p.counters + slot, (unsigned int)(p.cpi * (rd + 1)));
+        const float inv = 1.f / (float)HW;
+        for (int ch = threadIdx.x; ch < C; ch += NC_THREADS) {
+            double ss = 0.0, qq = 0.0;
+            for (int k = 0; k < p.cpi; k++) {
+                float2 v = __ldcg(reinterpret_cast<const float2*>(pbuf + ((long)k * C + ch) * 2));
+                ss += (double)v.x;
+                qq += (double)v.y;
+            }
+            const float fs = (float)ss, fq = (float)qq;
+            s_m1[ch] = fs * inv;
+            s_m2[ch] = fq * inv;
+            if (j == 0 && p.d_adain) {
+                p.d_adain[(long)gb * p.P + p.off + ch] = fs;      // d beta  ("mean" columns)
+                p.d_adain[(long)gb * p.P + p.off + C + ch] = fq;  // d gamma ("std" columns)
+            }
+        }
+        __syncthreads();
+        const float4 m1 = *reinterpret_cast<const float4*>(s_m1 + c), m2 = *reinterpret_cast<const float4*>(s_m2 + c);
+        // ---- pass 2: dy = gamma*rstd * (g1 - mean(g1) - xhat * mean(g1*xhat)); y and dz are L2 hits
+        for (int r = r0 + lm.rl; r < r1; r += NC_U * lm.rowl) {
+            float4 vv[NC_U], gg[NC_U];
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr < r1) {
+                    vv[u] = ld_cg4(yb + (long)rr * C);
+                    gg[u] = coop_load_dz(p, gb, rr, c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NC_U; u++) {
+                const int rr = r + u * lm.rowl;
+                if (rr >= r1) break;
+                float4 v = vv[u], g1 = gg[u];
+                if (p.act == CG_ACT_RELU) {
+                    if (fmaf(v.x, a.x, b.x) <= 0.f) g1.x = 0.f;
+                    if (fmaf(v.y, a.y, b.y) <= 0.f) g1.y = 0.f;
+                    if (fmaf(v.z, a.z, b.z) <= 0.f) g1.z = 0.f;
+                    if (fmaf(v.w, a.w, b.w) <= 0.f) g1.w = 0.f;
+                }
+                float4 o;
+                o.x = a.x * (g1.x - m1.x - (v.x - mu.x) * rs.x * m2.x);
+                o.y = a.y * (g1.y - m1.y - (v.y - mu.y) * rs.y * m2.y);
+                o.z = a.z * (g1.z - m1.z - (v.z - mu.z) * rs.z * m2.z);
+                o.w = a.w * (g1.w - m1.w - (v.w - mu.w) * rs.w * m2.w);
+                *reinterpret_cast<float4*>(p.dy + ((long)gb * HW + rr) * C + c) = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+static int g_coop_slots = 0;          // co-resident CTAs of the cooperative kernels on this device
+static long g_coop_budget = 0;        // bytes of instances kept in flight (L2-resident between the two passes)
+
+static int coop_init() {
+    if (g_coop_slots) return CG_OK;
+    int dev = 0, sms = 0, per_f = 0, per_b = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, norm_coop_fwd_kernel, NC_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, norm_coop_bwd_kernel, NC_THREADS, 0);
+    if (e != cudaSuccess || per_f < 1 || per_b < 1) {
+        set_error("norm_coop: occupancy query failed (%s)", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    int per = per_f < per_b ? per_f : per_b;
+    if (per > 1) per = 1;  // one 512-thread CTA per SM (128 registers per thread: 8 + 8 float4 loads in flight without spills)
+    g_coop_slots = sms * per;
+    const char* mb = getenv("COUNCIL_NORM_L2_MB");  // measurement switch: bytes of instances in flight (default 64 MB of the 126 MB L2)
+    g_coop_budget = (long)(mb ? atoi(mb) : 64) << 20;
+    return CG_OK;
+}
+
+// concurrent instances: the largest divisor of NI (no partially filled rounds) whose in-flight bytes fit the budget
+static void coop_shape(int NI, long inst_bytes, int& conc, int& cpi) {
+    conc = 1;
+    for (int cnd = 1; cnd <= NI && cnd <= g_coop_slots && cnd <= 256; cnd++)  // 256 counters in the first KB of the workspace
+        if (NI % cnd == 0 && (long)cnd * inst_bytes <= g_coop_budget) conc = cnd;
+    cpi = g_coop_slots / conc;
+    if (cpi > 64) cpi = 64;  // finalise cost grows with cpi; 64 slices of a large map are plenty
+}
+
+size_t norm_coop_ws(int NI, int C) {
+    if (coop_init()) return 0;
+    // counters (one cache line per slot is not needed: one word each) + double-buffered partials for the worst shape
+    return 1024 + (size_t)2 * g_coop_slots * C * 2 * sizeof(float);
+}
+
+static int check_cc(int C) {
+    CG_REQUIRE(C % 4 == 0 && C <= 256 && NC_THREADS % (C / 4) == 0, "norm_coop: unsupported channel count %d", C);
+    return CG_OK;
+}
+
+}  // namespace cg
+
+using namespace cg;
+
+extern "C" size_t cg_norm_fused_workspace_bytes(int G, int B, int C) { return norm_coop_ws(G * B, C); }
+
+extern "C" int cg_norm_fused_fwd(const float* y, const float* adain, int P, int off, const float* res, float* z, float* mean,
+                                 float* rstd, int G, int B, int H, int W, int C, int act, int ups, float eps, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    if (int rc = check_cc(C)) return rc;
+    if (int rc = coop_init()) return rc;
+    CG_REQUIRE(act == CG_ACT_NONE || act == CG_ACT_RELU, "norm_fused_fwd: activation %d unsupported", act);
+    size_t need = norm_coop_ws(G * B, C);
+    if (need > ws_bytes) {
+        set_error("norm_fused_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+        return CG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CoopP p{};
+    p.y = y; p.adain = adain; p.res = res; p.z = z; p.mean_out = mean; p.rstd_out = rstd;
+    p.NI = G * B; p.P = P; p.off = off; p.H = H; p.W = W; p.C = C; p.act = act; p.ups = ups; p.eps = eps;
+    coop_shape(p.NI, (long)H * W * C * 4, p.conc, p.cpi);
+    p.counters = (unsigned int*)ws;
+    p.part = (float*)((uint8_t*)ws + 1024);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 1024, st);
+    if (e != cudaSuccess) {
+        set_error("norm_fused_fwd: %s", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    norm_coop_fwd_kernel<<<p.conc * p.cpi, NC_THREADS, 0, st>>>(p);
+    return check_launch("norm_coop_fwd");
+}
+
+extern "C" int cg_norm_fused_bwd(const float* dz, const float* y, const float* mean, const float* rstd, const float* adain, int P,
+                                 int off, float* dy, float* d_adain, int G, int B, int H, int W, int C, int act, int ups,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = check_cc(C)) return rc;
+    if (int rc = coop_init()) return rc;
+    CG_REQUIRE(act == CG_ACT_NONE || act == CG_ACT_RELU, "norm_fused_bwd: activation %d unsupported", act);
+    size_t need = norm_coop_ws(G * B, C);
+    if (need > ws_bytes) {
+        set_error("norm_fused_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+        return CG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CoopP p{};
+    p.dz = dz; p.y = y; p.mean_in = mean; p.rstd_in = rstd; p.adain = adain; p.dy = dy; p.d_adain = adain ? d_adain : nullptr;
+    p.NI = G * B; p.P = P; p.off = off; p.H = H; p.W = W; p.C = C; p.act = act; p.ups = ups;
+    coop_shape(p.NI, (long)H * W * C * 4 * (ups ? 5 : 2), p.conc, p.cpi);
+    p.counters = (unsigned int*)ws;
+    p.part = (float*)((uint8_t*)ws + 1024);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 1024, st);
+    if (e != cudaSuccess) {
+        set_error("norm_fused_bwd: %s", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    norm_coop_bwd_kernel<<<p.conc * p.cpi, NC_THREADS, 0, st>>>(p);
+    return check_launch("norm_coop_bwd");
+}

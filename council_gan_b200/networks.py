@@ -231,6 +231,8 @@ class CouncilGen(_StackedNet):
         self.ops, self.hp, self.G = ops, hp, G
         # statistics in the convolution epilogue (cg_conv_fwd_stats) vs a separate pass; see profiles/r01_summary.md
         self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', '0') == '1'  # measured: +5.2 ms of epilogue vs -2.6 ms saved -> off by default
+        # single-launch normalisation with L2-resident second pass (default); COUNCIL_COOP_NORM=0 selects the two- / three-kernel forms
+        self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '1') == '1'
         self.dim, self.style_dim, self.nd, self.nr, self.mlp_dim = g['dim'], g['style_dim'], g['n_downsample'], g['n_res'], g['mlp_dim']
         dim, nd, nr = self.dim, self.nd, self.nr
         img_lanes = [0, 1, 2]
@@ -344,13 +346,17 @@ class CouncilGen(_StackedNet):
         w, b = self._w(s, sl)
         # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
         # ups_in (no-grad passes): the x2 nearest upsample is folded into this convolution (four 2x2 parity classes)
+        off = self.adain_off.get(s.key, 0)
         if self.fuse_stats:
             y, mean, rstd = ops.conv_fwd_stats(x, w, s.stride, s.pad, ups=ups_in)
+            z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
+        elif self.coop_norm:  # statistics + normalise in one launch, second pass over y from L2 (csrc/norm_coop.cu)
+            y = ops.conv_fwd(x, w, None, s.stride, s.pad, ups=ups_in)
+            z, mean, rstd = ops.norm_fused_fwd(y, adain, off, res, act, ups_out)
         else:
             y = ops.conv_fwd(x, w, None, s.stride, s.pad, ups=ups_in)
             mean, rstd = ops.in_stats(y)
-        off = self.adain_off.get(s.key, 0)
-        z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
+            z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
         if saved is not None:
             saved.append((x, y, mean, rstd))
         return z
@@ -361,7 +367,8 @@ class CouncilGen(_StackedNet):
         ops = self.ops
         x, y, mean, rstd = rec
         off = self.adain_off.get(s.key, 0)
-        dy = ops.norm_act_bwd(dz, y, mean, rstd, adain, off, act, ups_out, d_adain)
+        norm_bwd = ops.norm_fused_bwd if self.coop_norm else ops.norm_act_bwd
+        dy = norm_bwd(dz, y, mean, rstd, adain, off, act, ups_out, d_adain)
         ops.conv_wgrad(x, dy, self.bank.g(s.wname), None, s.stride, s.pad)
         if not need_dx:
             return None

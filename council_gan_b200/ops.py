@@ -63,6 +63,9 @@ _SIGS = {
     'cg_in_stats': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_norm_act_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp]),
     'cg_norm_act_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp, C.c_size_t, _fp]),
+    'cg_norm_fused_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp] + [C.c_int] * 7 + [C.c_float, _fp, C.c_size_t, _fp]),
+    'cg_norm_fused_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp] + [C.c_int] * 7 + [_fp, C.c_size_t, _fp]),
+    'cg_norm_fused_workspace_bytes': (C.c_size_t, [C.c_int] * 3),
     'cg_upsample2x_bwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_mask_head_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_mask_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
@@ -308,6 +311,37 @@ class CudaOps:
                         lambda: self._ck(self.lib.cg_norm_act_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
                                                                   G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
                                          'cg_norm_act_bwd'))
+        return dy
+
+    # single-launch forms (csrc/norm_coop.cu): HBM sees y once, the second pass is served from L2
+    def norm_fused_fwd(self, y, adain=None, off=0, res=None, act=ACT_NONE, ups=False, eps=1e-5):
+        """statistics + normalise (+AdaIN affine, +activation, +residual, +x2 upsample) in ONE launch -> (z, mean, rstd)"""
+        self._chk(y, adain, res)
+        G, B, H, W, Cc = y.shape
+        z = self.empty(G, B, 2 * H if ups else H, 2 * W if ups else W, Cc)
+        mean, rstd = self.empty(G, B, Cc), self.empty(G, B, Cc)
+        P = adain.shape[-1] if adain is not None else 0
+        ws = self._ws_for(self.lib.cg_norm_fused_workspace_bytes(G, B, Cc))
+        units = 1 + (1 if res is not None else 0) + (4 if ups else 1)  # HBM: read y once (+ residual), write z (x4 when upsampling)
+        self._timed_raw('hbm:norm_fused_fwd G%d B%d %dx%d C%d%s%s' % (G, B, H, W, Cc, ' res' if res is not None else '', ' ups' if ups else ''),
+                        4.0 * units * y.numel(),
+                        lambda: self._ck(self.lib.cg_norm_fused_fwd(_p(y), _p(adain), P, off, _p(res), _p(z), _p(mean), _p(rstd), G, B, H, W, Cc,
+                                                                    act, int(bool(ups)), eps, _p(ws), ws.numel(), self._stream()),
+                                         'cg_norm_fused_fwd'))
+        return z, mean, rstd
+
+    def norm_fused_bwd(self, dz, y, mean, rstd, adain=None, off=0, act=ACT_NONE, ups=False, d_adain=None):
+        """both reductions + apply of the normalisation backward in ONE launch -> dy (d_adain columns overwritten)"""
+        self._chk(dz, y, mean, rstd, adain, d_adain)
+        G, B, H, W, Cc = y.shape
+        dy = self.empty(G, B, H, W, Cc)
+        P = adain.shape[-1] if adain is not None else 0
+        ws = self._ws_for(self.lib.cg_norm_fused_workspace_bytes(G, B, Cc))
+        units = 1 + (4 if ups else 1) + 1  # HBM: read y and dz once, write dy
+        self._timed_raw('hbm:norm_fused_bwd G%d B%d %dx%d C%d%s' % (G, B, H, W, Cc, ' ups' if ups else ''), 4.0 * units * y.numel(),
+                        lambda: self._ck(self.lib.cg_norm_fused_bwd(_p(dz), _p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(dy), _p(d_adain),
+                                                                    G, B, H, W, Cc, act, int(bool(ups)), _p(ws), ws.numel(), self._stream()),
+                                         'cg_norm_fused_bwd'))
         return dy
 
     def upsample2x_bwd(self, d_up):

@@ -105,6 +105,18 @@ int cg_norm_act_bwd(const float* dz, const float* y, const float* mean, const fl
                     const float* adain, int P, int off, float* dy, float* d_adain, int G, int B,
                     int H, int W, int C, int act, int ups, void* ws, size_t ws_bytes, void* stream);
 
+/* Single-launch forms of the three calls above (csrc/norm_coop.cu): statistics + normalise in ONE kernel, and the whole
+ * backward in ONE kernel; a launch keeps only as many instances in flight as fit in L2, so the second pass over y (and dz)
+ * is served from L2 and HBM sees y once.  Same results as cg_in_stats + cg_norm_act_fwd / cg_norm_act_bwd; mean / rstd
+ * [G][B][C] are also written by the forward (the backward needs them).  ws >= cg_norm_fused_workspace_bytes(). */
+int cg_norm_fused_fwd(const float* y, const float* adain, int P, int off, const float* res, float* z, float* mean,
+                      float* rstd, int G, int B, int H, int W, int C, int act, int ups, float eps, void* ws,
+                      size_t ws_bytes, void* stream);
+int cg_norm_fused_bwd(const float* dz, const float* y, const float* mean, const float* rstd, const float* adain, int P,
+                      int off, float* dy, float* d_adain, int G, int B, int H, int W, int C, int act, int ups, void* ws,
+                      size_t ws_bytes, void* stream);
+size_t cg_norm_fused_workspace_bytes(int G, int B, int C);
+
 /* backward of nn.Upsample(scale_factor=2) (networks.py:385): dx[N][H][W][C] = 2x2 fan-in sum of d_up[N][2H][2W][C] */
 int cg_upsample2x_bwd(const float* d_up, float* dx, int N, int H, int W, int C, void* stream);
 
