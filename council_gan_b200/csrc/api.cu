@@ -131,6 +131,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
     g_wgrad_2cta = ((mode >> 16) & 1) ? 0 : 1;  // bit 16: one weight-gradient CTA per SM (default: two co-resident CTAs)
     g_wgrad_xm2 = ((mode >> 18) & 1) ? 0 : 1;   // bit 18: one x-on-M weight-gradient CTA per SM
     g_fwd_2cta = ((mode >> 17) & 1) ? 0 : 1;    // bit 17: one forward / dgrad CTA per SM for tiles <= 64 wide (default: two co-resident)
+    g_img_path = ((mode >> 19) & 1) ? 0 : 1;    // bit 19: image-side layers on the older paths (TMA im2col forward, explicit patch matrix weight gradient)
     g_pair_cap = (mode >> 8) & 0xff;  // bits 8..15: cap on the number of CTA pairs launched (0 = as many as are co-resident)
     return prev;
 }
@@ -153,6 +154,7 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     // the same predicates as the dispatch in cg_conv_fwd / cg_conv_wgrad (the forward's activation is not known here: a tanh
     // layer falls through to the direct path, so the larger of the two needs is reported)
     const bool patch_fwd = which == 0 && (g_tc_mode & 1) && patch_path(*g) && g->KH * g->KW >= 16;
+    if (which == 2 && (g_tc_mode & 4) && img_wgrad_supported(*g)) return img_wgrad_ws(*g);
     const bool patch_wgrad = which == 2 && (g_tc_mode & 4) && patch_path(*g);
     if (patch_fwd || patch_wgrad) {
         cg_conv_geom p = patch_geom(*g);
@@ -180,6 +182,7 @@ extern "C" int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w
                            float slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((g_tc_mode & 1) && img_fwd_supported(*g, act)) return img_conv_fwd(*g, x, w, bias, y, act, slope, st);
     // forward: the patch matrix pays off when there are many taps (7x7: 49, 4x4: 16); the 3x3 pair layer is faster
     // straight through TMA im2col with 32-byte rows (measured 3.1 ms vs 4.7 ms at B=40, 256x256)
     if ((g_tc_mode & 1) && patch_path(*g) && g->KH * g->KW >= 16 && act != CG_ACT_TANH) {
@@ -221,6 +224,7 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
                              size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((g_tc_mode & 4) && img_wgrad_supported(*g)) return img_conv_wgrad(*g, x, dy, dw, db, ws, ws_bytes, st);
     if ((g_tc_mode & 4) && patch_path(*g)) {
         size_t need = cg_conv_workspace_bytes(g, 2);
         if (need > ws_bytes) {

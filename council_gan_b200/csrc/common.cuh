@@ -1,5 +1,6 @@
 // Shared helpers for libcouncil_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -92,5 +93,16 @@ bool tc_wgrad_supported(const cg_conv_geom& g);
 size_t tc_wgrad_ws(const cg_conv_geom& g);
 int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
+
+int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp);
+int tc_sm_count();
+
+// ---- image-side convolutions (<= 8 input lanes, 64 output channels) with patches built in shared memory (conv_img.cu) ----
+bool img_fwd_supported(const cg_conv_geom& g, int act);
+int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, int act, float slope, cudaStream_t st);
+bool img_wgrad_supported(const cg_conv_geom& g);
+size_t img_wgrad_ws(const cg_conv_geom& g);
+int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+extern int g_img_path;
 
 }  // namespace cg

@@ -28,6 +28,7 @@
 //
 // Reference call sites replaced: nn.Conv2d forward (networks.py:513,516) and cuDNN dgrad via autograd.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cstdlib>
 #include <cstdio>
 #include <cuda.h>
@@ -71,138 +72,6 @@ static void init_driver() {
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDriverGetVersion(&g_driver_version);
     });
-}
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int n,
-                                                   uint16_t off_w, uint16_t off_h) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::
-            "r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;            // leading byte offset (ignored for swizzled K-major; canonical value 1)
-    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row core-matrix groups
-    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-    return d;
-}
-// K-major rows of 8 fp32 (32 bytes), 32-byte swizzle (cute Layout_K_SW32): 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;  // SWIZZLE_32B
-    return d;
-}
-// instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Column sums over the 32 rows held by the 32 lanes of a warp: a[j] of lane r is element (row r, column j); on return
-// lane j holds the sum of column j.  Transpose-reduce butterfly: at step `off` every lane keeps the half of its columns
-// selected by its lane bit and receives the partner's partial for that half -> 16+8+4+2+1 = 31 shuffles.
-__device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; i++) {
-            float send = upper ? a[i] : a[i + off];
-            float keep = upper ? a[i + off] : a[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return a[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1158,15 +1027,6 @@ struct WgParams {
 // 4 K-rows x 128 B with 32-byte chunks XOR-ed by the row index (Swizzle<2,5,2>) = TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
 // descriptor layout type SWIZZLE_128B_BASE32B (1).  LBO = stride between 32-element MN groups, SBO = stride
 // between 4-row K groups (512 B); one K=8 MMA consumes two K groups.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
-    return d;
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1781,6 +1641,30 @@ size_t tc_wgrad_ws(const cg_conv_geom& g) {
     wg_plan(g, splits, chunk);
     if (splits == 1) return 0;
     return (size_t)splits * g.G * g.Cout * g.KH * g.KW * g.Cin * sizeof(float);
+}
+
+// dy [rows][C] as a 2-D tensor map with 32-channel x kp-pixel boxes in the MN-major TF32 layout (also used by conv_img.cu)
+int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp) {
+    init_driver();
+    if (!g_encode_tiled) {
+        set_error("cuTensorMapEncodeTiled unavailable");
+        return CG_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)kp};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(mn-major map rows=%ld C=%d) failed: %d", rows, C, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+int tc_sm_count() {
+    init_driver();
+    return g_sm_count;
 }
 
 int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {

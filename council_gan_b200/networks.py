@@ -231,8 +231,9 @@ class CouncilGen(_StackedNet):
         self.ops, self.hp, self.G = ops, hp, G
         # statistics in the convolution epilogue (cg_conv_fwd_stats) vs a separate pass; see profiles/r01_summary.md
         self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', '0') == '1'  # measured: +5.2 ms of epilogue vs -2.6 ms saved -> off by default
-        # single-launch normalisation with L2-resident second pass (default); COUNCIL_COOP_NORM=0 selects the two- / three-kernel forms
-        self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '1') == '1'
+        # single-launch normalisation with L2-resident second pass (csrc/norm_coop.cu): correct and tested, but measured equal to the
+        # two- / three-kernel forms inside the step (profiles/r02_runB_*), so it is opt-in: COUNCIL_COOP_NORM=1
+        self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '0') == '1'
         self.dim, self.style_dim, self.nd, self.nr, self.mlp_dim = g['dim'], g['style_dim'], g['n_downsample'], g['n_res'], g['mlp_dim']
         dim, nd, nr = self.dim, self.nd, self.nr
         img_lanes = [0, 1, 2]

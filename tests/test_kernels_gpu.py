@@ -79,17 +79,25 @@ CONV_CASES = [
     ('patch_disc0_3x3_pair', 2, 2, 2, 16, 16, 8, 64, 3, 1, 1, False),
     ('patch_dis0_4x4s2_img', 2, 2, 4, 16, 16, 4, 64, 4, 2, 1, False),
     ('patch_enc0_7x7_shared', 3, 1, 2, 16, 16, 4, 64, 7, 1, 3, False),
+    # shared-memory patch builder: several tiles per CTA, image borders inside tiles, weight-gradient CTAs with no work
+    ('img_disc0_3x3_pair_multi', 3, 3, 5, 32, 32, 8, 64, 3, 1, 1, False),
+    ('img_dis0_4x4s2_rect', 2, 2, 3, 32, 64, 4, 64, 4, 2, 1, False),
 ]
 
 
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64 | (1 << 16), 7 | (1 << 17)])
+@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64 | (1 << 16), 7 | (1 << 17), 7 | (1 << 19)])
 def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
     """tc = 0: SIMT fp32; 1: the default tensor-core dispatch; 7|32|64|1<<16: the switchable variants that are off by default --
     CTA pairs (cta_group::2) for 64-wide forward tiles and in the weight gradient, one weight-gradient CTA per SM instead of the default two;
     7|1<<17: ONE forward / data-gradient CTA per SM for tiles <= 64 channels wide (the default co-schedules two)."""
     name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups = case
-    if tc > 1 and not (name.startswith('tc_') and (Cout % 128 == 0 or Cout <= 64 or Cin <= 64)):
+    if tc == 7 | (1 << 19):
+        # image-side layers: the default is the shared-memory patch builder (csrc/conv_img.cu); bit 19 selects the older
+        # TMA-im2col forward / explicit-patch weight gradient, which stay tested
+        if not (Cin <= 8 and Cout == 64 and K * K * Cin <= 96):
+            pytest.skip('not an image-side layer')
+    elif tc > 1 and not (name.startswith('tc_') and (Cout % 128 == 0 or Cout <= 64 or Cin <= 64)):
         pytest.skip('no optional variant for this geometry')
     ops.set_tensor_core_mode(tc)
     tol = 2e-5 if tc == 0 else 4e-3
