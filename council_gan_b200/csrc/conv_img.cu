@@ -40,6 +40,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
+template <int L, int KW>
 __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1k(smem_raw);
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP
     if (warp < IMG_BUILD_THREADS / 32) {
         // ===================== patch builders: thread = one pixel row of the tile; group gq builds tiles gq, gq+2, ... ===========
         const int gq = warp >> 2, t = threadIdx.x & 127;
-        const int L = p.L;
+        constexpr int TAPS = KW * KW, NV = TAPS * (L / 4);  // float4 loads per pixel: all issued before the first use
         int it = gq;
         for (int tile = cidx + gq * p.cpg; tile < tiles; tile += 2 * p.cpg, it += 2) {
             const int stage = it % p.stages;
@@ -102,29 +103,21 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP
             const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
             const float* xb = p.x + ((long)(g * p.xg_images + img) * p.H * p.W) * L;
             const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+            float4 v[NV];
+#pragma unroll
+            for (int tap = 0; tap < TAPS; tap++) {
+                const int iy = iy0 + tap / KW, ix = ix0 + tap % KW;
+                const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const float* px = xb + ((long)iy * p.W + ix) * L;
+#pragma unroll
+                for (int h = 0; h < L / 4; h++) v[tap * (L / 4) + h] = in ? ldg4(px + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             mbar_wait(&a_empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * a_stage + (t >> 3) * 1024 + (t & 7) * 128;
             const int sw = t & 7;
-            int tap = 0;
-            for (int kh = 0; kh < p.KH; kh++) {
-                const int iy = iy0 + kh;
-                for (int kw = 0; kw < p.KW; kw++, tap++) {
-                    const int ix = ix0 + kw;
-                    const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                    const float* px = xb + ((long)iy * p.W + ix) * L;
-                    if (L == 8) {
-                        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                        if (in) { v0 = ldg4(px); v1 = ldg4(px + 4); }
-                        uint8_t* dst = sa + (tap >> 2) * 16384;
-                        const int u = (tap & 3) * 2;
-                        *reinterpret_cast<float4*>(dst + ((u ^ sw) << 4)) = to_tf32(v0);
-                        *reinterpret_cast<float4*>(dst + (((u + 1) ^ sw) << 4)) = to_tf32(v1);
-                    } else {
-                        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (in) v0 = ldg4(px);
-                        *reinterpret_cast<float4*>(sa + (tap >> 3) * 16384 + (((tap & 7) ^ sw) << 4)) = to_tf32(v0);
-                    }
-                }
+#pragma unroll
+            for (int q = 0; q < NV; q++) {  // 16-byte unit q of the pixel's K row: chunk q / 8, swizzled slot (q % 8) ^ (row % 8)
+                *reinterpret_cast<float4*>(sa + (q >> 3) * 16384 + (((q & 7) ^ sw) << 4)) = to_tf32(v[q]);
             }
             fence_proxy_async();
             mbar_arrive(&a_full[stage]);
@@ -209,6 +202,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP
 // weight (+ bias) gradient
 // =====================================================================================================================
 // stage = [4 M groups of 32 k-rows][kp pixels x 128 B] (patches, built here) + [2 N groups of 32 couts][kp x 128 B] (dy, TMA)
+template <int L, int KW, int KP>
 __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_wgrad_kernel(const __grid_constant__ ImgP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1k(smem_raw);
@@ -250,45 +244,52 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_wgrad_kernel(const __
     if (warp < IMG_BUILD_THREADS / 32) {
         // ===================== builders: 128 threads per stage = (pixel, half of the taps); groups alternate stages ===============
         const int gq = warp >> 2, t = threadIdx.x & 127;
-        const int L = p.L, taps = p.KH * p.KW;
-        const int tpp = 128 / p.kp;             // threads per pixel (2 at kp = 64)
-        const int px_i = t / tpp, sub = t - px_i * tpp;
+        constexpr int TAPS = KW * KW;
+        constexpr int TPP = 128 / KP;                     // threads per pixel (2 at 64 pixels per stage)
+        constexpr int MYT = (TAPS + TPP - 1) / TPP;       // taps per thread: sub, sub + TPP, ...
+        const int px_i = t / TPP, sub = t - px_i * TPP;
         const int sw = px_i & 3;
         const uint32_t row_off = (uint32_t)((px_i >> 2) * 512 + (px_i & 3) * 128);
         for (int it = gq; it < nst; it += 2) {
             const int stage = it % p.stages;
             const uint32_t phase = (uint32_t)((it / p.stages) & 1);
-            const long m = mbeg + (long)it * p.kp + px_i;
+            const long m = mbeg + (long)it * KP + px_i;
             const int img = (int)(m / pq);
             const int rem = (int)(m - (long)img * pq);
             const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
             const float* xb = p.x + ((long)(g * p.xg_images + img) * p.H * p.W) * L;
             const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+            float4 v[MYT * (L / 4)];
+#pragma unroll
+            for (int j = 0; j < MYT; j++) {  // all loads of this thread's taps in flight before the first store
+                const int tap = sub + j * TPP;
+                const int iy = iy0 + tap / KW, ix = ix0 + tap % KW;
+                const bool in = tap < TAPS && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const float* px = xb + ((long)iy * p.W + ix) * L;
+#pragma unroll
+                for (int h = 0; h < L / 4; h++) v[j * (L / 4) + h] = in ? ldg4(px + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
             if (t == 0) {  // dy boxes of this stage; the expect_tx arrival comes last (below), so the phase cannot complete early
-                const int row = (int)((long)g * p.Mpix + mbeg + (long)it * p.kp);
+                const int row = (int)((long)g * p.Mpix + mbeg + (long)it * KP);
                 tma_load_2d(&p.dymap, &full[stage], sa + 4 * box, 0, row);
                 tma_load_2d(&p.dymap, &full[stage], sa + 5 * box, 32, row);
             }
-            for (int tap = sub; tap < taps; tap += tpp) {
-                const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                const int iy = iy0 + kh, ix = ix0 + kw;
-                const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                const float* px = xb + ((long)iy * p.W + ix) * L;
-                if (L == 8) {
-                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                    if (in) { v0 = ldg4(px); v1 = ldg4(px + 4); }
-                    uint8_t* dst = sa + (tap >> 2) * box + row_off + (((tap & 3) ^ sw) << 5);
-                    *reinterpret_cast<float4*>(dst) = to_tf32(v0);
-                    *reinterpret_cast<float4*>(dst + 16) = to_tf32(v1);
-                } else {
-                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in) v0 = ldg4(px);
-                    *reinterpret_cast<float4*>(sa + (tap >> 3) * box + row_off + ((((tap & 7) >> 1) ^ sw) << 5) + (tap & 1) * 16) = to_tf32(v0);
+#pragma unroll
+            for (int j = 0; j < MYT; j++) {
+                const int tap = sub + j * TPP;
+                if (tap < TAPS) {
+                    if (L == 8) {  // k = 8 tap: M group tap / 4, 32-byte chunk tap % 4
+                        uint8_t* dst = sa + (tap >> 2) * box + row_off + (((tap & 3) ^ sw) << 5);
+                        *reinterpret_cast<float4*>(dst) = to_tf32(v[j * (L / 4)]);
+                        *reinterpret_cast<float4*>(dst + 16) = to_tf32(v[j * (L / 4) + (L / 4 - 1)]);
+                    } else {       // k = 4 tap: M group tap / 8, 32-byte chunk (tap % 8) / 2, half tap % 2
+                        *reinterpret_cast<float4*>(sa + (tap >> 3) * box + row_off + ((((tap & 7) >> 1) ^ sw) << 5) + (tap & 1) * 16) = to_tf32(v[j]);
+                    }
                 }
             }
-            if (sub == tpp - 1) {  // row K of the patch matrix = 1: its accumulator row is the bias gradient
+            if (sub == TPP - 1) {  // row K of the patch matrix = 1: its accumulator row is the bias gradient
                 const int kk = p.K & 31;
                 *reinterpret_cast<float*>(sa + (p.K >> 5) * box + row_off + (((kk >> 3) ^ sw) << 5) + (kk & 7) * 4) = 1.0f;
             }
@@ -370,6 +371,7 @@ static bool img_geom_ok(const cg_conv_geom& g) {
     if (!g_img_path) return false;
     if (g.Cout != 64 || (g.Cin != 4 && g.Cin != 8) || g.ups || g.KH != g.KW) return false;
     if (g.stride != 1 && g.stride != 2) return false;
+    if (!((g.Cin == 8 && g.KH == 3) || (g.Cin == 4 && g.KH == 4))) return false;  // the two instantiated layer types
     const int K = g.KH * g.KW * g.Cin;
     if (K > 96) return false;
     if (((long)g.B * g.Ho * g.Wo) % 128 != 0) return false;
@@ -401,16 +403,17 @@ int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const fl
     const long tiles = p.Mpix / 128;
     if (p.cpg > tiles) p.cpg = (int)tiles;
     size_t smem = (size_t)stages * a_stage + (size_t)p.KC * 8192 + (2 * stages + 4) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(img_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    auto kern = p.L == 8 ? img_conv_fwd_kernel<8, 3> : img_conv_fwd_kernel<4, 4>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[p.L == 8]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(img_conv_fwd_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set = true;
+        attr_set[p.L == 8] = true;
     }
-    img_conv_fwd_kernel<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
+    kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
     return check_launch("img_conv_fwd");
 }
 
@@ -428,7 +431,7 @@ int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float
         set_error("conv_wgrad(image path): workspace %zu < %zu bytes", ws_bytes, need);
         return CG_ERR_WORKSPACE;
     }
-    p.kp = p.Mpix % 64 == 0 ? 64 : 32;
+    p.kp = 64;  // img_wgrad_supported() guarantees Mpix % 128 == 0
     if (int rc = tc_encode_mn_map(&p.dymap, dy, (long)g.G * p.Mpix, 64, p.kp)) return rc;
     p.x = x; p.part = (float*)ws;
     const long nstage_total = p.Mpix / p.kp;
@@ -439,16 +442,17 @@ int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float
     if (stages > 6) stages = 6;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + (2 * stages + 2) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(img_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    auto kern = p.L == 8 ? img_conv_wgrad_kernel<8, 3, 64> : img_conv_wgrad_kernel<4, 4, 64>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[p.L == 8]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(img_conv_wgrad_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set = true;
+        attr_set[p.L == 8] = true;
     }
-    img_conv_wgrad_kernel<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
+    kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
     if (int rc = check_launch("img_conv_wgrad")) return rc;
     const int total = g.G * (p.K + 1) * 64;
     img_wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.part, dw, db, g.G, p.K, p.cpg);

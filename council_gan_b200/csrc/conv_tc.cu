@@ -448,6 +448,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     uint64_t* tfull_bar = empty_bar + p.stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // 4 x (32 x 36) floats, only carved when p.stats
 
     const int pq = p.P * p.Q;
     const int PT = (p.B * pq + 2 * TC_BM - 1) / (2 * TC_BM);  // pair tiles (256 pixels) per (group, class)
@@ -585,6 +586,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             for (int c0 = 0; c0 < p.bn; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (p.stats) {
+                    // instance-norm statistics of the raw output in the epilogue (Conv2d -> InstanceNorm2d / AdaIN, networks.py:516-518):
+                    // this CTA's 128 rows are one 128-pixel tile inside one image (P*Q % 256 == 0); same scheme as conv_tc_kernel.
+                    // On the wide layers served by this kernel the main loop of the next tile (tens of thousands of cycles) hides it.
+                    float* patch = stat_smem + quad * (32 * 36);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<float4*>(patch + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    float cs = 0.f, cq = 0.f;
+#pragma unroll
+                    for (int r2 = 0; r2 < 32; r2++) {
+                        float e = patch[r2 * 36 + lane];
+                        cs += e;
+                        cq = fmaf(e, e, cq);
+                    }
+                    const int tiles_per_img = pq / TC_BM;
+                    const int mt = pt * 2 + (int)rank;
+                    const int img = (mt * TC_BM) / pq;
+                    const int chunk = ((c * tiles_per_img + (mt - img * tiles_per_img)) << 2) + quad;
+                    const long col = (long)(g * p.B + img) * p.Cout + nt * p.bn + c0 + lane;
+                    if (mt * TC_BM < p.B * pq) *reinterpret_cast<float2*>(p.stats + ((long)chunk * p.stats_gbc + col) * 2) = make_float2(cs, cq);
+                }
                 if (valid) {
                     if (p.bias) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
@@ -743,8 +768,8 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     long tiles = (long)p.G * p.ncls * ((p.Cout + p.bn - 1) / p.bn) * MT;
     // CTA pairs (cta_group::2): one MMA spans two SMs, each staging its own 128 pixel rows and HALF of the weight rows -> less
     // shared-memory operand traffic per SM (wide layers) and half the MMA instructions per pixel (narrow layers, issue-bound)
-    if (((p.bn == 256 && (g_pair_mode & 1)) || (p.bn == 128 && (g_pair_mode & 2)) || (p.bn == 64 && (g_pair_mode & 4))) && p.bk == 32 && p.Cout % p.bn == 0 && p.Cin % 32 == 0 && !p.stats &&
-        p.act != CG_ACT_TANH && (long)p.B * p.P * p.Q >= 512) {
+    if (((p.bn == 256 && (g_pair_mode & 1)) || (p.bn == 128 && (g_pair_mode & 2)) || (p.bn == 64 && (g_pair_mode & 4))) && p.bk == 32 && p.Cout % p.bn == 0 && p.Cin % 32 == 0 &&
+        (!p.stats || (p.P * p.Q) % (2 * TC_BM) == 0) && p.act != CG_ACT_TANH && (long)p.B * p.P * p.Q >= 512) {
         static bool attr2_set = false;
         if (!attr2_set) {
             cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -755,10 +780,10 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
             attr2_set = true;
         }
         const int stage2 = p.cps * (TC_BM * TC_BK * 4 + (p.bn / 2) * TC_BK * 4);
-        int stages2 = (226 * 1024 - 1536) / stage2;
+        int stages2 = (226 * 1024 - 1536 - stat_bytes) / stage2;
         if (stages2 > TC2_MAX_STAGES) stages2 = TC2_MAX_STAGES;
         p.stages = stages2;
-        size_t smem2 = (size_t)stages2 * stage2 + 1024 + (2 * TC2_MAX_STAGES + 4) * 8 + 32;
+        size_t smem2 = (size_t)stages2 * stage2 + 1024 + (2 * TC2_MAX_STAGES + 4) * 8 + 32 + stat_bytes;
         static int max_pairs = 0;  // co-resident CTA pairs (GPCs with an odd SM count strand one SM each)
         if (!max_pairs) {
             cudaLaunchConfig_t cfg = {};

@@ -230,7 +230,10 @@ class CouncilGen(_StackedNet):
         assert input_dim == 3 and g['num_of_mask_dim_to_add'] == 3, 'mask head kernel is specialised for RGB + 3 masks'
         self.ops, self.hp, self.G = ops, hp, G
         # statistics in the convolution epilogue (cg_conv_fwd_stats) vs a separate pass; see profiles/r01_summary.md
-        self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', '0') == '1'  # measured: +5.2 ms of epilogue vs -2.6 ms saved -> off by default
+        # '1': every normalised layer; 'auto' (default): the wide layers (>= 128 output channels, K >= 1024), whose main loop is an order of
+        # magnitude longer than the epilogue and hides the reduction; '0': never.  Round 1 measured +5.2 ms with '1' (narrow 256x256 layers
+        # are epilogue-bound); the CTA-pair kernel that serves the wide layers gained the statistics epilogue in round 2.
+        self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', 'auto')
         # single-launch normalisation with L2-resident second pass (csrc/norm_coop.cu): correct and tested, but measured equal to the
         # two- / three-kernel forms inside the step (profiles/r02_runB_*), so it is opt-in: COUNCIL_COOP_NORM=1
         self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '0') == '1'
@@ -348,7 +351,8 @@ class CouncilGen(_StackedNet):
         # the bias of a convolution that feeds IN / AdaIN is removed again by the mean subtraction: skip the add
         # ups_in (no-grad passes): the x2 nearest upsample is folded into this convolution (four 2x2 parity classes)
         off = self.adain_off.get(s.key, 0)
-        if self.fuse_stats:
+        wide = s.cout >= 128 and s.k * s.k * s.cin >= 1024
+        if self.fuse_stats == '1' or (self.fuse_stats == 'auto' and wide and not self.coop_norm):
             y, mean, rstd = ops.conv_fwd_stats(x, w, s.stride, s.pad, ups=ups_in)
             z = ops.norm_act_fwd(y, mean, rstd, adain, off, res, act, ups_out)
         elif self.coop_norm:  # statistics + normalise in one launch, second pass over y from L2 (csrc/norm_coop.cu)

@@ -332,7 +332,7 @@ class Council_Trainer(nn.Module):
                 continue
             if not any(net is n for n, _ in self._pending.get(fam, [])):
                 self._reduce_async(fam, net)
-        if not (defer and self.world > 1):
+        if not (defer and self.world > 1) or os.environ.get('COUNCIL_DP_SYNC') == '1':  # COUNCIL_DP_SYNC=1: A/B switch, join immediately
             self._finish(fam)
 
     def _src(self, d, a, b):
@@ -561,8 +561,9 @@ class Council_Trainer(nn.Module):
             if d_x is None:
                 d_x = ops.zeros(*rec['x_fake'].shape)
             gen.backward(d_x, d_mask, rec['enc'], rec['dec'],
-                         on_decoder_done=(lambda g=gen: self._reduce_async('gen', g, g.enc_end, None)) if self.world > 1 else None)
-            if self.world > 1:
+                         on_decoder_done=(lambda g=gen: self._reduce_async('gen', g, g.enc_end, None))
+                         if self.world > 1 and os.environ.get('COUNCIL_DP_SYNC') != '1' else None)
+            if self.world > 1 and os.environ.get('COUNCIL_DP_SYNC') != '1':
                 self._reduce_async('gen', gen, 0, gen.enc_end)  # encoder bucket; the decoder bucket went out during the encoder backward
         self._adam('gen', defer=True)  # joined at the start of the next update (or by save / state_dict / sample)
         self._enc_cache.clear()

@@ -22,6 +22,7 @@ def run(xa, xb):
     load_states(tr, states)
     co.seed_all(gold['rng_seed'])
     tr.dis_update(xa, xb, hp); tr.dis_council_update(xa, xb, hp); tr.gen_update(xa, xb, hp, gold['iteration'])
+    tr.synchronize()  # under data parallelism the last family's all-reduce + Adam are deferred
     torch.cuda.synchronize()
     return tr
 

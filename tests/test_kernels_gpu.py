@@ -141,6 +141,10 @@ STATS_CASES = [
     ('stats_up_classes', 2, 2, 2, 16, 16, 128, 64, 3, 1, 1, True),
     ('stats_first_7x7_patch', 2, 1, 2, 16, 16, 4, 64, 7, 1, 3, False),
     ('stats_small_map_simt', 2, 2, 1, 8, 8, 256, 256, 3, 1, 1, False),
+    # CTA-pair kernel with the statistics epilogue (round 2): 256- and 128-wide tiles, the production residual-block shape
+    ('stats_pair_128_wide', 2, 2, 2, 32, 32, 128, 128, 3, 1, 1, False),
+    ('stats_pair_down_128_256', 2, 2, 2, 32, 32, 128, 256, 4, 2, 1, False),
+    ('stats_prod_res_3x3_256', 4, 4, 8, 64, 64, 256, 256, 3, 1, 1, False),
 ]
 
 
