@@ -95,6 +95,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
                   cudaStream_t st);
 
 int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp);
+int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_rows);
 int tc_sm_count();
 
 // ---- image-side convolutions (<= 8 input lanes, 64 output channels) with patches built in shared memory (conv_img.cu) ----

@@ -26,10 +26,10 @@ constexpr int IMG_MMA_WARP = 8;
 constexpr int IMG_THREADS = IMG_BUILD_THREADS + 32 + 128;  // + MMA warp + 4 epilogue warps (warp % 4 = TMEM lane quadrant)
 
 struct ImgP {
-    CUtensorMap dymap;   // (wgrad) dy [G*Mpix][64] as 32-channel x kp-pixel MN-major boxes
+    CUtensorMap dymap;   // (wgrad) dy [G*Mpix][64] as 32-channel x kp-pixel MN-major boxes; (forward) y [G*Mpix][64] store map, 32 x 128 boxes
     const float* x; const float* w; const float* bias; float* y; float* part;
     int G, xg_images, B, H, W, L, Ho, Wo, KH, KW, stride, pad;
-    int K, KC, k8, stages, act, cpg, kp;
+    int K, KC, k8, stages, act, cpg, kp, nsbuf;
     float slope;
     long Mpix, chunk;
 };
@@ -41,13 +41,14 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // forward
 // =====================================================================================================================
 template <int L, int KW>
-__global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP p) {
+__global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const __grid_constant__ ImgP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1k(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_stage = p.KC * 16384;                 // KC chunks of [128 rows x 128 B]
     uint8_t* sB = smem + (size_t)p.stages * a_stage;  // KC chunks of [64 rows x 128 B]
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.KC * 8192);
+    uint8_t* sStage = sB + (size_t)p.KC * 8192;       // nsbuf output tiles: 2 chunks of [128 rows x 128 B], 128-byte swizzled
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(sStage + (size_t)p.nsbuf * 32768);
     uint64_t* a_empty = a_full + p.stages;
     uint64_t* tfull = a_empty + p.stages;
     uint64_t* tempty = tfull + 2;
@@ -152,18 +153,28 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP
             }
         }
     } else {
-        // ===================== epilogue: bias + activation, one pixel row (64 channels = 256 B) per thread =====================
+        // ===================== epilogue: bias + activation -> swizzled shared-memory tile -> TMA tensor store =====================
+        // Direct global stores from the accumulator layout (thread = pixel row, 16 bytes per lane at a 256-byte stride) touch 32
+        // half-written sectors per instruction and cap at ~2 TB/s (ncu, profiles/r02_runD_*): the tile goes through shared memory
+        // in the 128-byte-swizzled layout (conflict-free for row-per-thread writes) and leaves as two bulk tensor stores.
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        int acc = 0;
+        const bool issuer = warp == IMG_MMA_WARP + 1 && lane == 0;
+        int acc = 0, sbuf = 0;
         uint32_t acc_phase = 0;
         const float* bp = p.bias ? p.bias + (long)g * 64 : nullptr;
+        const int sw = row & 7;
         for (int tile = cidx; tile < tiles; tile += p.cpg) {
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const long m = (long)tile * 128 + row;
-            float* yp = p.y + ((long)g * p.B * pq + m) * 64;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 64);
+            // the staging buffer about to be overwritten must have been read out by its previous store
+            if (issuer) {
+                if (p.nsbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            uint8_t* stg = sStage + (size_t)sbuf * 32768 + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 float v[32];
@@ -183,12 +194,24 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const ImgP
                     for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
                 }
 #pragma unroll
-                for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(yp + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<float4*>(stg + (c0 >> 5) * 16384 + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may start the tile after next
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (issuer) {
+                const int grow = (int)((long)g * p.B * pq + (long)tile * 128);  // first output row (pixel) of the tile
+                const uint32_t src = smem_u32(sStage + (size_t)sbuf * 32768);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&p.dymap), "r"(0), "r"(grow), "r"(src) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&p.dymap), "r"(32), "r"(grow), "r"(src + 16384) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (++sbuf == p.nsbuf) sbuf = 0;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -397,12 +420,15 @@ int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const fl
     fill_common(p, g);
     p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act; p.slope = slope;
     const int a_stage = p.KC * 16384;
-    int stages = (226 * 1024 - p.KC * 8192 - 2048) / a_stage;
+    // output staging: two 32 KB tiles when at least three operand stages still fit, else one
+    p.nsbuf = (226 * 1024 - p.KC * 8192 - 2048 - 2 * 32768) / a_stage >= 3 ? 2 : 1;
+    int stages = (226 * 1024 - p.KC * 8192 - 2048 - p.nsbuf * 32768) / a_stage;
     if (stages > 6) stages = 6;
     p.stages = stages;
     const long tiles = p.Mpix / 128;
     if (p.cpg > tiles) p.cpg = (int)tiles;
-    size_t smem = (size_t)stages * a_stage + (size_t)p.KC * 8192 + (2 * stages + 4) * 8 + 16 + 1024;
+    if (int rc = tc_encode_store_map(&p.dymap, y, (long)g.G * p.Mpix, 64, 128)) return rc;
+    size_t smem = (size_t)stages * a_stage + (size_t)p.KC * 8192 + (size_t)p.nsbuf * 32768 + (2 * stages + 4) * 8 + 16 + 1024;
     auto kern = p.L == 8 ? img_conv_fwd_kernel<8, 3> : img_conv_fwd_kernel<4, 4>;
     static bool attr_set[2] = {false, false};
     if (!attr_set[p.L == 8]) {

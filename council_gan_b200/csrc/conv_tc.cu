@@ -1687,6 +1687,26 @@ int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp)
     }
     return CG_OK;
 }
+// y [rows][C] fp32 as a 2-D store map with 32-channel x box_rows boxes, 128-byte swizzled shared-memory side (epilogues that stage
+// their tile in shared memory and leave through cp.async.bulk.tensor stores)
+int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_rows) {
+    init_driver();
+    if (!g_encode_tiled) {
+        set_error("cuTensorMapEncodeTiled unavailable");
+        return CG_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(store map rows=%ld C=%d) failed: %d", rows, C, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
 int tc_sm_count() {
     init_driver();
     return g_sm_count;

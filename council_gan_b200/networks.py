@@ -237,6 +237,7 @@ class CouncilGen(_StackedNet):
         # single-launch normalisation with L2-resident second pass (csrc/norm_coop.cu): correct and tested, but measured equal to the
         # two- / three-kernel forms inside the step (profiles/r02_runB_*), so it is opt-in: COUNCIL_COOP_NORM=1
         self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '0') == '1'
+        self.fuse_head = os.environ.get('COUNCIL_FUSE_HEAD', '1') == '1'  # decoder tail of no-grad passes as one kernel (csrc/head_fused.cu)
         self.dim, self.style_dim, self.nd, self.nr, self.mlp_dim = g['dim'], g['style_dim'], g['n_downsample'], g['n_res'], g['mlp_dim']
         dim, nd, nr = self.dim, self.nd, self.nr
         img_lanes = [0, 1, 2]
@@ -420,6 +421,14 @@ class CouncilGen(_StackedNet):
             x = self._conv_norm(x, blk[1], sl, adain, ACT_NONE, res, r == nres - 1 and nup > 0 and not fold, saved)
         for u, (a, b) in enumerate(self.dec_up):
             x = self._conv_norm(x, a, sl, adain, ACT_RELU, None, False, saved, ups_in=fold)
+            if fold and u + 1 == nup and self.fuse_head and b.cout == 64 and ops.head_fused_supported((1, 1, x.shape[2], x.shape[3], 64)):
+                # no-grad pass: the rest of the decoder (AdaIN + ReLU of this block, the three 1x1 head layers, mask compositing)
+                # is one kernel; the 64-channel full-resolution map is read once instead of making four HBM round trips
+                w, _ = self._w(b, sl)
+                y = ops.conv_fwd(x, w, None, b.stride, b.pad)
+                mean, rstd = ops.in_stats(y)
+                (w1, b1), (w2, b2), (w3, b3) = (self._w(s, sl) for s in self.head)
+                return ops.head_fused(y, mean, rstd, adain, self.adain_off[b.key], w1, b1, w2, b2, w3, b3, x_img)
             x = self._conv_norm(x, b, sl, adain, ACT_RELU, None, u + 1 < nup and not fold, saved)
         acts = [x]
         for li, s in enumerate(self.head):

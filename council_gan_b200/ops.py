@@ -68,6 +68,7 @@ _SIGS = {
     'cg_norm_fused_workspace_bytes': (C.c_size_t, [C.c_int] * 3),
     'cg_upsample2x_bwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_mask_head_fwd': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_head_fused': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int] + [_fp] * 9 + [C.c_int] * 3 + [_fp]),
     'cg_mask_head_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_avgpool_fwd': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'cg_avgpool_bwd': (C.c_int, [_fp, _fp] + [C.c_int] * 7 + [_fp]),
@@ -360,6 +361,23 @@ class CudaOps:
         self._ck(self.lib.cg_mask_head_fwd(_p(h), _p(x_in), _p(x_fake), _p(mask), G, B, H * W, self._stream()),
                  'cg_mask_head_fwd')
         return x_fake, mask
+
+    def head_fused(self, y, mean, rstd, adain, off, w1, b1, w2, b2, w3, b3, x_in):
+        """AdaIN + ReLU of the last 3x3 block, the three 1x1 head convolutions and the mask compositing in ONE launch
+        (no-grad decoder passes): y [G,B,H,W,64] raw conv output -> (x_fake, mask) [G,B,H,W,4]"""
+        self._chk(y, mean, rstd, adain, w1, b1, w2, b2, w3, b3, x_in)
+        G, B, H, W, Cc = y.shape
+        assert Cc == 64 and tuple(w1.shape[1:]) == (64, 1, 1, 64) and tuple(w3.shape[1:]) == (12, 1, 1, 64)
+        x_fake, mask = self.empty(G, B, H, W, 4), self.empty(G, B, H, W, 4)
+        P = adain.shape[-1] if adain is not None else 0
+        self._timed_raw('hbm:head_fused G%d B%d %dx%d' % (G, B, H, W), 4.0 * (y.numel() + 3 * x_fake.numel()),
+                        lambda: self._ck(self.lib.cg_head_fused(_p(y), _p(mean), _p(rstd), _p(adain), P, off, _p(w1), _p(b1), _p(w2), _p(b2),
+                                                                _p(w3), _p(b3), _p(x_in), _p(x_fake), _p(mask), G, B, H * W, self._stream()),
+                                         'cg_head_fused'))
+        return x_fake, mask
+
+    def head_fused_supported(self, y_shape):
+        return y_shape[-1] == 64 and (y_shape[2] * y_shape[3]) % 128 == 0
 
     def mask_head_bwd(self, h, x_in, d_xfake, d_mask=None):
         self._chk(h, x_in, d_xfake, d_mask)

@@ -129,6 +129,14 @@ int cg_mask_head_fwd(const float* h, const float* x_in, float* x_fake, float* ma
 int cg_mask_head_bwd(const float* h, const float* x_in, const float* d_xfake, const float* d_mask,
                      float* dh_pre, int G, int B, int HW, void* stream);
 
+/* The decoder tail of a no-grad pass in ONE launch (csrc/head_fused.cu): y[G][B][HW][64] = raw output of the last 3x3 block;
+ * z = relu(AdaIN(y)) -> 1x1 64->64 + relu (w1, b1) -> 1x1 64->64 + relu (w2, b2) -> 1x1 64->12 + tanh (w3, b3) -> mask
+ * compositing with x_in (cg_mask_head_fwd).  Weights [G][Cout][64], HW % 128 == 0.  Replaces cg_norm_act_fwd + 3 x cg_conv_fwd +
+ * cg_mask_head_fwd (Decoder_V2_atten, networks.py:391-407) when nothing has to be kept for a backward pass. */
+int cg_head_fused(const float* y, const float* mean, const float* rstd, const float* adain, int P, int off, const float* w1,
+                  const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, const float* x_in,
+                  float* x_fake, float* mask, int G, int B, int HW, void* stream);
+
 /* ---- image-space helpers ---------------------------------------------------------------------- */
 /* nn.AvgPool2d(3, 2, padding=1, count_include_pad=False), networks.py:32,129 */
 int cg_avgpool_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);

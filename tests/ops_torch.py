@@ -160,6 +160,15 @@ class TorchOps:
         pad = torch.zeros_like(im[..., :1])
         return torch.cat((im, pad), -1).contiguous(), torch.cat((mask, pad), -1).contiguous()
 
+    def head_fused(self, y, mean, rstd, adain, off, w1, b1, w2, b2, w3, b3, x_in):
+        z = self.norm_act_fwd(y, mean, rstd, adain, off, None, ACT_RELU, False)
+        z = self.conv_fwd(z, w1, b1, 1, 0, act=ACT_RELU)
+        z = self.conv_fwd(z, w2, b2, 1, 0, act=ACT_RELU)
+        return self.mask_head_fwd(self.conv_fwd(z, w3, b3, 1, 0, act=ACT_TANH), x_in)
+
+    def head_fused_supported(self, y_shape):
+        return y_shape[-1] == 64
+
     def mask_head_bwd(self, h, x_in, d_xfake, d_mask=None):
         # h is the tanh OUTPUT of the last conv; return the gradient w.r.t. its pre-activation
         pre = torch.atanh(h.detach().double().clamp(-1 + 1e-15, 1 - 1e-15)).requires_grad_(True)

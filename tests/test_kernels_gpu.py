@@ -262,6 +262,34 @@ def test_mask_head(ops, ref):
         check(got, want, 5e-5, 'mask head bwd')
 
 
+@pytest.mark.parametrize('shape', [(2, 2, 16, 16), (4, 8, 256, 256), (3, 1, 8, 48)])
+@pytest.mark.parametrize('adain_on', [True, False])
+def test_head_fused(ops, ref, shape, adain_on):
+    """cg_head_fused (AdaIN + ReLU -> 1x1 -> 1x1 -> 1x1 tanh -> mask compositing in one tcgen05 kernel) against the float64
+    composition of the separate ops, and against the separate CUDA ops it replaces."""
+    G, B, H, W = shape
+    y = rnd(G, B, H, W, 64, seed=1, scale=1.5) + 0.2
+    P, off = 4 * 64 + 8, 4
+    adain = rnd(G, B, P, seed=2) if adain_on else None
+    w1, w2 = rnd(G, 64, 1, 1, 64, seed=3, scale=0.15), rnd(G, 64, 1, 1, 64, seed=4, scale=0.15)
+    w3 = rnd(G, 12, 1, 1, 64, seed=5, scale=0.1)
+    b1, b2, b3 = rnd(G, 64, seed=6, scale=0.1), rnd(G, 64, seed=7, scale=0.1), rnd(G, 12, seed=8, scale=0.1)
+    x_in = rnd(1, B, H, W, 4, seed=9)
+    x_in[..., 3] = 0
+    mean, rstd = ops.in_stats(y)
+    xf, mask = ops.head_fused(y, mean, rstd, adain, off, w1, b1, w2, b2, w3, b3, x_in)
+    rxf, rmask = ref.head_fused(d(y), d(mean), d(rstd), d(adain), off, d(w1), d(b1), d(w2), d(b2), d(w3), d(b3), d(x_in))
+    # three chained TF32 GEMMs feeding tanh(10 tanh(.)): compare at the TF32 tolerance on O(1) outputs
+    assert (xf.double() - rxf).abs().max().item() < 2e-2 and (xf.double() - rxf).abs().mean().item() < 1e-3
+    assert (mask.double() - rmask).abs().max().item() < 2e-2 and (mask.double() - rmask).abs().mean().item() < 1e-3
+    assert float(xf[..., 3].abs().max()) == 0 and float(mask[..., 3].abs().max()) == 0
+    # the separate tensor-core kernels round the same way: much tighter agreement
+    z = ops.norm_act_fwd(y, mean, rstd, adain, off, None, 1, False)
+    z = ops.conv_fwd(ops.conv_fwd(z, w1, b1, 1, 0, act=1), w2, b2, 1, 0, act=1)
+    sxf, smask = ops.mask_head_fwd(ops.conv_fwd(z, w3, b3, 1, 0, act=3), x_in)
+    assert (xf - sxf).abs().mean().item() < 2e-4 and (mask - smask).abs().mean().item() < 2e-4
+
+
 def test_image_helpers(ops, ref):
     G, B, H, W = 2, 3, 8, 12
     x = rnd(G, B, H, W, 8, seed=1)
