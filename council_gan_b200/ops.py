@@ -171,7 +171,10 @@ class CudaOps:
     def launch_count(self):
         return int(self.lib.cg_launch_count())
 
+    _tc_mode = 1
+
     def set_tensor_core_mode(self, mode):
+        self._tc_mode = int(mode)
         return self.lib.cg_set_tensor_core_mode(int(mode))
 
     # -- live per-kernel timing (bench.py roofline): CUDA events on the launching stream ----------
@@ -377,7 +380,8 @@ class CudaOps:
         return x_fake, mask
 
     def head_fused_supported(self, y_shape):
-        return y_shape[-1] == 64 and (y_shape[2] * y_shape[3]) % 128 == 0
+        # a tcgen05 (TF32) kernel: not used when the exact-fp32 SIMT mode is selected (cg_set_tensor_core_mode(0))
+        return (self._tc_mode & 1) == 1 and y_shape[-1] == 64 and (y_shape[2] * y_shape[3]) % 128 == 0
 
     def mask_head_bwd(self, h, x_in, d_xfake, d_mask=None):
         self._chk(h, x_in, d_xfake, d_mask)
