@@ -371,6 +371,29 @@ def main():
                         'bytes_per_launch': h_bytes, 'launches': h_cnt, 'avg_ms': h_ms / h_cnt, 'share_of_step': h_ms / ms,
                         'all_hbm_kernels_ms_per_step': round(sum(v[0] for v in hbm_times.values()) / args.steps, 3),
                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth)' if peaks else 'fallback 6500'}
+    # MEASURED_PEAKS.json has no TF32 figure: measure the library TF32 GEMM on this box (cuBLAS through torch.matmul, 8192^3, best of
+    # 10 after warm-up) as a second, like-for-like denominator for the TF32 convolution kernels
+    tf32_lib = None
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ma = torch.randn(8192, 8192, device=dev)
+        mb = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            torch.matmul(ma, mb)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(ma, mb)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tf32_lib = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del ma, mb
+    except Exception:
+        pass
     if ktimes:
         key, (tot_ms, cnt, flops) = max(ktimes.items(), key=lambda kv: kv[1][0])
         tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2.0  # TF32 runs at half the bf16 tensor rate
@@ -383,6 +406,7 @@ def main():
             pass
         roofline = {'bound': 'tensor', 'kernel': key, 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
                     'frac_of_nominal_tf32_1100': ach / 1100.0, 'flops_per_launch': flops,
+                    'tf32_cublas_tflops_measured_here': tf32_lib, 'frac_of_tf32_cublas': (ach / tf32_lib) if tf32_lib else None,
                     'traffic': traffic, 'tensor_pipe_pct_ncu': tensor_pipe, 'launches': cnt, 'avg_ms': tot_ms / cnt, 'share_of_step': tot_ms / ms,
                     'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 operands)' if peaks else 'fallback 1400/2')}
     alg_tflop = 2 * ALG_GMAC_PER_IMAGE_MEMBER_256 * 1e9 * scale * n_members * batch * world / 1e12
