@@ -154,6 +154,8 @@ extern "C" size_t cg_conv_workspace_bytes(const cg_conv_geom* g, int which) {
     // the same predicates as the dispatch in cg_conv_fwd / cg_conv_wgrad (the forward's activation is not known here: a tanh
     // layer falls through to the direct path, so the larger of the two needs is reported)
     const bool patch_fwd = which == 0 && (g_tc_mode & 1) && patch_path(*g) && g->KH * g->KW >= 16;
+    if (which == 2 && small_wgrad_supported(*g)) return small_ws(*g, 2);
+    if (which == 1 && small_dgrad_supported(*g)) return small_ws(*g, 1);
     if (which == 2 && (g_tc_mode & 4) && img_wgrad_supported(*g)) return img_wgrad_ws(*g);
     const bool patch_wgrad = which == 2 && (g_tc_mode & 4) && patch_path(*g);
     if (patch_fwd || patch_wgrad) {
@@ -182,6 +184,7 @@ extern "C" int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w
                            float slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (small_fwd_supported(*g, act)) return small_conv_fwd(*g, x, w, bias, y, st);
     if ((g_tc_mode & 1) && img_fwd_supported(*g, act)) return img_conv_fwd(*g, x, w, bias, y, act, slope, st);
     // forward: the patch matrix pays off when there are many taps (7x7: 49, 4x4: 16); the 3x3 pair layer is faster
     // straight through TMA im2col with 32-byte rows (measured 3.1 ms vs 4.7 ms at B=40, 256x256)
@@ -209,6 +212,7 @@ extern "C" int cg_conv_dgrad(const cg_conv_geom* g, const float* dy, const float
                              const float* mask_src, float mask_slope, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (small_dgrad_supported(*g)) return small_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, ws, ws_bytes, st);
     if ((g_tc_mode & 2) && tc_dgrad_supported(*g)) return tc_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, ws, ws_bytes, st);
     if (!g->ups) return simt_conv_dgrad(*g, dy, w, dx, addend, mask_src, mask_slope, st);
     size_t need = cg_conv_workspace_bytes(g, 1);
@@ -224,6 +228,7 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
                              size_t ws_bytes, void* stream) {
     if (int rc = validate_geom(*g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (small_wgrad_supported(*g)) return small_conv_wgrad(*g, x, dy, dw, db, ws, ws_bytes, st);
     if ((g_tc_mode & 4) && img_wgrad_supported(*g)) return img_conv_wgrad(*g, x, dy, dw, db, ws, ws_bytes, st);
     if ((g_tc_mode & 4) && patch_path(*g)) {
         size_t need = cg_conv_workspace_bytes(g, 2);

@@ -106,4 +106,14 @@ size_t img_wgrad_ws(const cg_conv_geom& g);
 int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
 extern int g_img_path;
 
+// ---- vector-shaped layers (512 -> 1 patch heads, the MLP's wide output layer) as streaming fp32 kernels (conv_small.cu) ----
+bool small_fwd_supported(const cg_conv_geom& g, int act);
+bool small_dgrad_supported(const cg_conv_geom& g);
+bool small_wgrad_supported(const cg_conv_geom& g);
+size_t small_ws(const cg_conv_geom& g, int which);
+int small_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int small_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float* dx, const float* addend, const float* mask_src,
+                     float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+int small_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace cg

@@ -54,6 +54,9 @@ CONV_CASES = [
     ('dis_out_1x1', 2, 2, 4, 4, 4, 512, 1, 1, 1, 0, False),
     ('mlp_linear', 2, 1, 3, 1, 1, 64, 256, 1, 1, 0, False),
     ('mlp_linear_big', 2, 2, 3, 1, 1, 256, 5888, 1, 1, 0, False),
+    ('mlp_linear_big_b8', 4, 4, 8, 1, 1, 256, 5888, 1, 1, 0, False),
+    ('dis_out_1x1_b32', 4, 4, 32, 32, 32, 512, 1, 1, 1, 0, False),
+    ('dis_out_1x1_c256_odd', 3, 3, 5, 7, 9, 256, 1, 1, 1, 0, False),
     ('odd_sizes', 1, 1, 1, 10, 14, 8, 20, 3, 1, 1, False),
     # shapes that qualify for the tcgen05 path (>= 128 output pixels per member)
     ('tc_res_3x3_256', 2, 2, 2, 16, 16, 256, 256, 3, 1, 1, False),
