@@ -312,15 +312,19 @@ def main():
 
     for _ in range(max(args.warmup, 0)):
         step(xa_d, xb_d)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler = ClockSampler(local_rank)  # every rank samples its own GPU: the step is power-limited and max-over-ranks timed
+    sampler.start()
     ops.start_timing()
     l0 = ops.launch_count()
     ms = timed(lambda: step(xa_d, xb_d), args.steps)
     launches = ops.launch_count() - l0
     ktimes = ops.stop_timing()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
+    if world > 1:  # median SM clock of every rank's GPU during the timed region (the slowest GPU sets the step time)
+        mhz = torch.tensor([float(clocks['sm_mhz'] or 0.0)], device=dev)
+        allm = [torch.zeros_like(mhz) for _ in range(world)]
+        dist.all_gather(allm, mhz)
+        clocks['sm_mhz_per_rank'] = [float(t.item()) for t in allm]
     ms_per_step = ms / args.steps
     value = batch * world / (ms_per_step * 1e-3)
 
