@@ -417,7 +417,7 @@ def main():
     line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'tf32' if args.tc else 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
-            'gpu_launches': int(launches), 'roofline': roofline, 'roofline_hbm': roofline_hbm,
+            'gpu_launches': int(launches), 'tensor_map_cache': ops.tensor_map_cache_stats(), 'roofline': roofline, 'roofline_hbm': roofline_hbm,
             'step_algorithmic_tflops': alg_tflop / (ms_per_step * 1e-3) / world,
             'kernel_times_ms_per_step': ({k: round(v[0] / args.steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:60]}
                                          if ktimes else None),

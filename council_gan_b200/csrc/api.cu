@@ -6,7 +6,7 @@ namespace cg {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-int g_tc_mode = 7;
+thread_local int g_tc_mode = 7;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -137,6 +137,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
 }
 
 extern "C" uint64_t cg_launch_count(void) { return g_launches.load(); }
+extern "C" void cg_tensor_map_cache_stats(uint64_t* hits, uint64_t* misses) { tc_map_cache_stats(hits, misses); }
 
 extern "C" int cg_zero(void* ptr, size_t bytes, void* stream) {
     cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);

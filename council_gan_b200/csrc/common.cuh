@@ -12,13 +12,27 @@ namespace cg {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
-extern int g_tc_mode;
-extern int g_pair_mode;
-extern int g_pair_cap;
-extern int g_wgrad_xm;
-extern int g_wgrad_2cta;
-extern int g_fwd_2cta;
-extern int g_wgrad_xm2;
+// kernel-selection switches of cg_set_tensor_core_mode: per calling THREAD (like cg_last_error), not process-global
+extern thread_local int g_tc_mode;
+extern thread_local int g_pair_mode;
+extern thread_local int g_pair_cap;
+extern thread_local int g_wgrad_xm;
+extern thread_local int g_wgrad_2cta;
+extern thread_local int g_fwd_2cta;
+extern thread_local int g_wgrad_xm2;
+
+constexpr int CG_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < CG_MAX_DEVICES ? dev : 0;
+}
+// true exactly once per (call site flag array, device): per-function attributes and occupancy queries are per device
+struct PerDeviceOnce {
+    std::atomic<bool> done[CG_MAX_DEVICES];
+    bool first() { return !done[current_device()].exchange(true); }
+    void reset() { done[current_device()].store(false); }
+};
 
 inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -97,6 +111,7 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
 int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp);
 int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_rows);
 int tc_sm_count();
+void tc_map_cache_stats(uint64_t* hits, uint64_t* misses);
 
 // ---- image-side convolutions (<= 8 input lanes, 64 output channels) with patches built in shared memory (conv_img.cu) ----
 bool img_fwd_supported(const cg_conv_geom& g, int act);
@@ -104,7 +119,7 @@ int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const fl
 bool img_wgrad_supported(const cg_conv_geom& g);
 size_t img_wgrad_ws(const cg_conv_geom& g);
 int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
-extern int g_img_path;
+extern thread_local int g_img_path;
 
 // ---- vector-shaped layers (512 -> 1 patch heads, the MLP's wide output layer) as streaming fp32 kernels (conv_small.cu) ----
 bool small_fwd_supported(const cg_conv_geom& g, int act);

@@ -19,7 +19,7 @@
 
 namespace cg {
 
-int g_img_path = 1;
+thread_local int g_img_path = 1;
 
 constexpr int IMG_BUILD_THREADS = 256;                 // two builder groups of 4 warps, alternating pipeline stages
 constexpr int IMG_MMA_WARP = 8;
@@ -430,14 +430,13 @@ int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const fl
     if (int rc = tc_encode_store_map(&p.dymap, y, (long)g.G * p.Mpix, 64, 128)) return rc;
     size_t smem = (size_t)stages * a_stage + (size_t)p.KC * 8192 + (size_t)p.nsbuf * 32768 + (2 * stages + 4) * 8 + 16 + 1024;
     auto kern = p.L == 8 ? img_conv_fwd_kernel<8, 3> : img_conv_fwd_kernel<4, 4>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[p.L == 8]) {
+    static PerDeviceOnce attr_once[2];
+    if (attr_once[p.L == 8].first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(img_conv_fwd_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set[p.L == 8] = true;
     }
     kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
     return check_launch("img_conv_fwd");
@@ -469,14 +468,13 @@ int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + (2 * stages + 2) * 8 + 16 + 1024;
     auto kern = p.L == 8 ? img_conv_wgrad_kernel<8, 3, 64> : img_conv_wgrad_kernel<4, 4, 64>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[p.L == 8]) {
+    static PerDeviceOnce attr_once[2];
+    if (attr_once[p.L == 8].first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(img_conv_wgrad_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set[p.L == 8] = true;
     }
     kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
     if (int rc = check_launch("img_conv_wgrad")) return rc;

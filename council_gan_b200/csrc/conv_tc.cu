@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <cuda.h>
 #include <mutex>
+#include <string.h>
 
 namespace cg {
 
@@ -47,16 +48,76 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
-static int g_sm_count = 0;
-int g_pair_cap = 0;
-int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
-int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
-int g_wgrad_xm2 = 1;   // ... also for the x-on-M kernel
-int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
-int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
+static int g_sm_count_dev[CG_MAX_DEVICES] = {0};  // multiprocessors per device ordinal
+static int sm_count_now() {
+    int dev = current_device();
+    if (!g_sm_count_dev[dev]) cudaDeviceGetAttribute(&g_sm_count_dev[dev], cudaDevAttrMultiProcessorCount, dev);
+    return g_sm_count_dev[dev];
+}
+thread_local int g_pair_cap = 0;
+thread_local int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
+thread_local int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
+thread_local int g_wgrad_xm2 = 1;   // ... also for the x-on-M kernel
+thread_local int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
+thread_local int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
                       // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
 static int g_driver_version = 0;
 static std::once_flag g_once;
+
+// ------------------------------------------------------------------------------------------------
+// tensor-map cache ("lazily-created TMA descriptor cache keyed by (ptr, shape), guarded by a mutex"): a training
+// step issues ~1500 cuTensorMapEncode* calls, almost all of them for (address, geometry) pairs seen in the previous step (the
+// caching allocator hands the same blocks out again); a direct-mapped table of encoded descriptors replaces the driver call by a
+// 48-byte key comparison and a 128-byte copy.  The descriptor depends on nothing but the key, so a stale entry is impossible.
+// ------------------------------------------------------------------------------------------------
+struct MapKey {
+    const void* ptr;
+    int64_t a, b;      // leading sizes (rows / images, ktot, ...)
+    int32_t v[8];      // remaining geometry: sizes, box, corners, stride, kind
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b && memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapSlot {
+    MapKey key;
+    CUtensorMap map;
+    bool used;
+};
+constexpr int MAP_SLOTS = 8192;
+static MapSlot* g_map_cache = nullptr;
+static std::mutex g_map_mutex;
+static std::atomic<uint64_t> g_map_hits{0}, g_map_misses{0};
+static inline uint32_t map_hash(const MapKey& k) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+    for (size_t i = 0; i < sizeof(MapKey); i++) h = (h ^ p[i]) * 1099511628211ull;
+    return (uint32_t)(h ^ (h >> 32)) & (MAP_SLOTS - 1);
+}
+// encode(map) is called on a miss; returns its status
+template <class F>
+static int cached_map(CUtensorMap* out, const MapKey& key, F encode) {
+    const uint32_t slot = map_hash(key);
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        if (!g_map_cache) g_map_cache = new MapSlot[MAP_SLOTS]();
+        MapSlot& s = g_map_cache[slot];
+        if (s.used && s.key == key) {
+            *out = s.map;
+            g_map_hits.fetch_add(1, std::memory_order_relaxed);
+            return CG_OK;
+        }
+    }
+    if (int rc = encode(out)) return rc;
+    g_map_misses.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    MapSlot& s = g_map_cache[slot];
+    s.key = key;
+    s.map = *out;
+    s.used = true;
+    return CG_OK;
+}
+void tc_map_cache_stats(uint64_t* hits, uint64_t* misses) {
+    *hits = g_map_hits.load();
+    *misses = g_map_misses.load();
+}
 
 static void init_driver() {
     std::call_once(g_once, [] {
@@ -67,9 +128,6 @@ static void init_driver() {
         fn = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
             g_encode_im2col = (EncodeIm2colFn)fn;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDriverGetVersion(&g_driver_version);
     });
 }
@@ -664,7 +722,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long ktot, int bn, int bk = TC_BK) {
+static int encode_weights_map_raw(CUtensorMap* map, const float* w, long rows, long ktot, int bn, int bk) {
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
     cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
@@ -679,6 +737,12 @@ static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long 
     return CG_OK;
 }
 
+static int encode_weights_map(CUtensorMap* map, const float* w, long rows, long ktot, int bn, int bk = TC_BK) {
+    MapKey k{};
+    k.ptr = w; k.a = rows; k.b = ktot; k.v[0] = bn; k.v[1] = bk; k.v[7] = 1;
+    return cached_map(map, k, [&](CUtensorMap* m) { return encode_weights_map_raw(m, w, rows, ktot, bn, bk); });
+}
+
 static int encode_weights_map_p(TcParams& p, const float* w, long rows, long ktot) {
     p.w_base = w;
     p.w_rows = rows;
@@ -688,8 +752,8 @@ static int encode_weights_map_p(TcParams& p, const float* w, long rows, long kto
 
 // activation [N][H][W][C] viewed by TMA as (C, W, H, N); bounding box corners as in CUTLASS
 // (cutlass/conv/collective/detail.hpp compute_lower/upper_corner_whd): lower = -pad_lo, upper = pad_hi - (K-1).
-static int encode_act_map(CUtensorMap* map, const float* x, long N, int H, int W, int C, int lo_w, int lo_h, int up_w, int up_h,
-                          int stride, int bk = TC_BK) {
+static int encode_act_map_raw(CUtensorMap* map, const float* x, long N, int H, int W, int C, int lo_w, int lo_h, int up_w, int up_h,
+                              int stride, int bk) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     int lower[2] = {lo_w, lo_h};
@@ -707,6 +771,14 @@ static int encode_act_map(CUtensorMap* map, const float* x, long N, int H, int W
     // cute/atom/copy_traits_sm90_im2col.hpp:477-483)
     if (g_driver_version <= 13010 && (long)N * H * W * C * 4 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
     return CG_OK;
+}
+
+static int encode_act_map(CUtensorMap* map, const float* x, long N, int H, int W, int C, int lo_w, int lo_h, int up_w, int up_h,
+                          int stride, int bk = TC_BK) {
+    MapKey k{};
+    k.ptr = x; k.a = N; k.b = ((int64_t)H << 32) | (uint32_t)W;
+    k.v[0] = C; k.v[1] = lo_w; k.v[2] = lo_h; k.v[3] = up_w; k.v[4] = up_h; k.v[5] = stride; k.v[6] = bk; k.v[7] = 2;
+    return cached_map(map, k, [&](CUtensorMap* m) { return encode_act_map_raw(m, x, N, H, W, C, lo_w, lo_h, up_w, up_h, stride, bk); });
 }
 
 static int pick_bn(int cout) {
@@ -754,15 +826,14 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     if (p.n_store == 0) p.n_store = p.bn;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 32 + stat_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set = true;
     }
     int MT = cdiv((long)p.B * p.P * p.Q, TC_BM);
     long tiles = (long)p.G * p.ncls * ((p.Cout + p.bn - 1) / p.bn) * MT;
@@ -770,24 +841,24 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     // shared-memory operand traffic per SM (wide layers) and half the MMA instructions per pixel (narrow layers, issue-bound)
     if (((p.bn == 256 && (g_pair_mode & 1)) || (p.bn == 128 && (g_pair_mode & 2)) || (p.bn == 64 && (g_pair_mode & 4))) && p.bk == 32 && p.Cout % p.bn == 0 && p.Cin % 32 == 0 &&
         (!p.stats || (p.P * p.Q) % (2 * TC_BM) == 0) && p.act != CG_ACT_TANH && (long)p.B * p.P * p.Q >= 512) {
-        static bool attr2_set = false;
-        if (!attr2_set) {
+        static PerDeviceOnce attr2_set;
+        if (attr2_set.first()) {
             cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(conv_tc2_kernel): %s", cudaGetErrorString(e));
                 return CG_ERR_CUDA;
             }
-            attr2_set = true;
         }
         const int stage2 = p.cps * (TC_BM * TC_BK * 4 + (p.bn / 2) * TC_BK * 4);
         int stages2 = (226 * 1024 - 1536 - stat_bytes) / stage2;
         if (stages2 > TC2_MAX_STAGES) stages2 = TC2_MAX_STAGES;
         p.stages = stages2;
         size_t smem2 = (size_t)stages2 * stage2 + 1024 + (2 * TC2_MAX_STAGES + 4) * 8 + 32 + stat_bytes;
-        static int max_pairs = 0;  // co-resident CTA pairs (GPCs with an odd SM count strand one SM each)
+        static int max_pairs_dev[CG_MAX_DEVICES] = {0};  // co-resident CTA pairs (GPCs with an odd SM count strand one SM each)
+        int& max_pairs = max_pairs_dev[current_device()];
         if (!max_pairs) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2 * (g_sm_count / 2));
+            cfg.gridDim = dim3(2 * (sm_count_now() / 2));
             cfg.blockDim = dim3(TC_THREADS);
             cfg.dynamicSmemBytes = 220 * 1024;
             cudaLaunchAttribute at;
@@ -801,9 +872,9 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
             cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_tc2_kernel, &cfg);
             if (e != cudaSuccess || n < 1) {
                 (void)cudaGetLastError();
-                n = g_sm_count / 2 - 4;
+                n = sm_count_now() / 2 - 4;
             }
-            max_pairs = n < g_sm_count / 2 ? n : g_sm_count / 2;
+            max_pairs = n < sm_count_now() / 2 ? n : sm_count_now() / 2;
         }
         int pairs = g_pair_cap > 0 && g_pair_cap < max_pairs ? g_pair_cap : max_pairs;
         if (int rc = encode_weights_map(&p.bmap, p.w_base, p.w_rows, p.w_ktot, p.bn / 2, 32)) return rc;  // each CTA stages half of the rows
@@ -812,7 +883,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
         conv_tc2_kernel<<<2 * nclusters, TC_THREADS, smem2, st>>>(p);
         return check_launch("conv_tc2_kernel");
     }
-    const long slots = (long)g_sm_count * (two ? 2 : 1);
+    const long slots = (long)sm_count_now() * (two ? 2 : 1);
     int grid = (int)(tiles < slots ? tiles : slots);
     if (p.bk == 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(p);
     else conv_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(p);
@@ -1630,7 +1701,7 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
         base = (long)g.G * ((rgs + tm * 4 - 1) / (tm * 4));
     }
     init_driver();
-    const int sms = (g_sm_count > 0 ? g_sm_count : 148) * (wg_two(g) ? 2 : 1) / (pair ? 2 : 1);
+    const int sms = (sm_count_now() > 0 ? sm_count_now() : 148) * (wg_two(g) ? 2 : 1) / (pair ? 2 : 1);
     long maxs = Mpix / (kp * 8);  // at least 8 pipeline stages of work per split
     if (maxs < 1) maxs = 1;
     if (maxs > 64) maxs = 64;
@@ -1669,7 +1740,7 @@ size_t tc_wgrad_ws(const cg_conv_geom& g) {
 }
 
 // dy [rows][C] as a 2-D tensor map with 32-channel x kp-pixel boxes in the MN-major TF32 layout (also used by conv_img.cu)
-int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp) {
+static int encode_mn_map_raw(CUtensorMap* map, const float* t, long rows, int C, int kp) {
     init_driver();
     if (!g_encode_tiled) {
         set_error("cuTensorMapEncodeTiled unavailable");
@@ -1687,9 +1758,14 @@ int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp)
     }
     return CG_OK;
 }
+int tc_encode_mn_map(CUtensorMap* map, const float* t, long rows, int C, int kp) {
+    MapKey k{};
+    k.ptr = t; k.a = rows; k.v[0] = C; k.v[1] = kp; k.v[7] = 3;
+    return cached_map(map, k, [&](CUtensorMap* m) { return encode_mn_map_raw(m, t, rows, C, kp); });
+}
 // y [rows][C] fp32 as a 2-D store map with 32-channel x box_rows boxes, 128-byte swizzled shared-memory side (epilogues that stage
 // their tile in shared memory and leave through cp.async.bulk.tensor stores)
-int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_rows) {
+static int encode_store_map_raw(CUtensorMap* map, float* t, long rows, int C, int box_rows) {
     init_driver();
     if (!g_encode_tiled) {
         set_error("cuTensorMapEncodeTiled unavailable");
@@ -1707,10 +1783,12 @@ int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_ro
     }
     return CG_OK;
 }
-int tc_sm_count() {
-    init_driver();
-    return g_sm_count;
+int tc_encode_store_map(CUtensorMap* map, float* t, long rows, int C, int box_rows) {
+    MapKey k{};
+    k.ptr = t; k.a = rows; k.v[0] = C; k.v[1] = box_rows; k.v[7] = 4;
+    return cached_map(map, k, [&](CUtensorMap* m) { return encode_store_map_raw(m, t, rows, C, box_rows); });
 }
+int tc_sm_count() { return sm_count_now(); }
 
 int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
     init_driver();
@@ -1724,34 +1802,30 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     p.bn = wg_bn(g.Cin);
     p.kp = wg_kp(g);
     p.Mpix = (long)g.B * g.Ho * g.Wo;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)g.Cout, (cuuint64_t)((long)g.G * p.Mpix)};
-        cuuint64_t strides[1] = {(cuuint64_t)g.Cout * 4};
-        cuuint32_t box[2] = {32, (cuuint32_t)p.kp};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode_tiled(&p.amap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)dy, dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r);
-            return CG_ERR_CUDA;
-        }
-    }
+    if (int rc = tc_encode_mn_map(&p.amap, dy, (long)g.G * p.Mpix, g.Cout, p.kp)) return rc;
     long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)nimg};
-        cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.W * g.Cin * 4, (cuuint64_t)g.H * g.W * g.Cin * 4};
-        int lower[2] = {-g.pad, -g.pad};
-        int upper[2] = {g.pad - (g.KW - 1), g.pad - (g.KH - 1)};
-        cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
-        CUresult r = g_encode_im2col(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, 32, p.kp, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeIm2col(x for wgrad) failed: %d", (int)r);
-            return CG_ERR_CUDA;
-        }
-        if (g_driver_version <= 13010 && nimg * g.H * g.W * g.Cin * 4 < 131072) reinterpret_cast<uint64_t*>(&p.bmap)[1] &= ~(1ull << 21);
+        MapKey k{};
+        k.ptr = x; k.a = nimg; k.b = ((int64_t)g.H << 32) | (uint32_t)g.W;
+        k.v[0] = g.Cin; k.v[1] = g.pad; k.v[2] = g.KW; k.v[3] = g.KH; k.v[4] = g.stride; k.v[5] = p.kp; k.v[7] = 5;
+        const int kp = p.kp;
+        int rc = cached_map(&p.bmap, k, [&](CUtensorMap* m) {
+            cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)nimg};
+            cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.W * g.Cin * 4, (cuuint64_t)g.H * g.W * g.Cin * 4};
+            int lower[2] = {-g.pad, -g.pad};
+            int upper[2] = {g.pad - (g.KW - 1), g.pad - (g.KH - 1)};
+            cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+            CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)x, dims, strides, lower, upper, 32, kp, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeIm2col(x for wgrad) failed: %d", (int)r);
+                return (int)CG_ERR_CUDA;
+            }
+            if (g_driver_version <= 13010 && nimg * g.H * g.W * g.Cin * 4 < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+            return (int)CG_OK;
+        });
+        if (rc) return rc;
     }
     p.G = g.G; p.xg_images = g.x_groups == 1 ? 0 : g.B;
     p.B = g.B; p.P = g.Ho; p.Q = g.Wo; p.Cin = g.Cin; p.Cout = g.Cout; p.KH = g.KH; p.KW = g.KW;
@@ -1768,18 +1842,17 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         if (stages > 8) stages = 8;
         p.stages = stages;
         size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
-        static bool attr3_set = false;
-        if (!attr3_set) {
+        static PerDeviceOnce attr3_set;
+        if (attr3_set.first()) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_xm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(wgrad_xm_kernel): %s", cudaGetErrorString(e));
                 return CG_ERR_CUDA;
             }
-            attr3_set = true;
         }
         int rgs = g.KH * g.KW * (g.Cin / 32);
         long units = (long)g.G * p.splits * ((rgs + p.Tm * 4 - 1) / (p.Tm * 4));
-        const int slots = g_sm_count * (two ? 2 : 1);
+        const int slots = sm_count_now() * (two ? 2 : 1);
         int grid = (int)(units < slots ? units : slots);
         if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_xm: units=%ld splits=%d chunk=%ld stages=%d Tm=%d kp=%d\n", units, p.splits, p.chunk, stages, p.Tm, p.kp);
         wgrad_xm_kernel<<<grid, TC_THREADS, smem, st>>>(p);
@@ -1797,17 +1870,16 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         if (stages > 8) stages = 8;
         p.stages = stages;
         size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
-        static bool attr2_set = false;
-        if (!attr2_set) {
+        static PerDeviceOnce attr2_set;
+        if (attr2_set.first()) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
                 set_error("cudaFuncSetAttribute(wgrad_tc2_kernel): %s", cudaGetErrorString(e));
                 return CG_ERR_CUDA;
             }
-            attr2_set = true;
         }
         long units = (long)g.G * (g.Cout / 256) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
-        int pairs = g_sm_count / 2;
+        int pairs = sm_count_now() / 2;
         int nclusters = (int)(units < pairs ? units : pairs);
         if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_tc2: units=%ld splits=%d chunk=%ld stages=%d T=%d bn=%d kp=%d\n", units, p.splits, p.chunk, stages, p.T, p.bn, p.kp);
         wgrad_tc2_kernel<<<2 * nclusters, TC_THREADS, smem, st>>>(p);
@@ -1827,17 +1899,16 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     int stages = ((two ? 100 : 200) * 1024) / stage_bytes;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(wgrad_tc_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set = true;
     }
     long units = (long)g.G * ((g.Cout + 127) / 128) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
-    const int slots = g_sm_count * (two ? 2 : 1);
+    const int slots = sm_count_now() * (two ? 2 : 1);
     int grid = (int)(units < slots ? units : slots);
     wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
     if (int rc = check_launch("wgrad_tc_kernel")) return rc;

@@ -223,14 +223,13 @@ extern "C" int cg_head_fused(const float* y, const float* mean, const float* rst
     const long tiles = (long)B * HW / 128;
     if (p.cpg > tiles) p.cpg = (int)tiles;
     const size_t smem = HD_A + 2 * HD_W + HD_W3 + (64 + 64 + 16) * 4 + 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaError_t e = cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(head_fused_kernel): %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        attr_set = true;
     }
     head_fused_kernel<<<G * p.cpg, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("head_fused");

@@ -54,6 +54,7 @@ _SIGS = {
     'cg_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'cg_set_tensor_core_mode': (C.c_int, [C.c_int]),
     'cg_launch_count': (C.c_uint64, []),
+    'cg_tensor_map_cache_stats': (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     'cg_conv_fwd': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_conv_fwd_stats': (C.c_int, [C.POINTER(ConvGeom), _fp, _fp, _fp, _fp, _fp, C.c_float, _fp, C.c_size_t, _fp]),
     'cg_conv_fwd_stats_workspace_bytes': (C.c_size_t, [C.POINTER(ConvGeom)]),
@@ -136,6 +137,7 @@ class CudaOps:
         # small per-step host data (style noise, peer index tables): ONE pinned staging buffer and ONE async H2D copy per
         # update instead of a pageable `torch.tensor(...).to(device)` (a hidden host sync) per table
         self._stage_ring = [None] * 8
+        self._ws_sizes = {}
         self._stage_next = 0
         # experimental (round 2, not yet measured): weight gradients on a side stream so that they overlap the HBM-bound passes of
         # the main stream.  bank.grad is written only by conv_wgrad and read only after wgrad_join() (trainer _adam).
@@ -149,6 +151,15 @@ class CudaOps:
     def _ck(self, rc, what):
         if rc != 0:
             raise RuntimeError('%s failed (%d): %s' % (what, rc, self.lib.cg_last_error().decode()))
+
+    def _conv_ws(self, g, which):
+        """Workspace of a convolution call; the size query is cached per (geometry, direction, kernel-selection mode)."""
+        key = (which, self._tc_mode, g.G, g.x_groups, g.B, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.KH, g.KW, g.stride, g.pad, g.ups)
+        n = self._ws_sizes.get(key)
+        if n is None:
+            n = int(self.lib.cg_conv_workspace_bytes(C.byref(g), which))
+            self._ws_sizes[key] = n
+        return self._ws_for(n)
 
     def _ws_for(self, nbytes):
         if nbytes > self._ws.numel():
@@ -170,6 +181,11 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.cg_launch_count())
+
+    def tensor_map_cache_stats(self):
+        h, m = C.c_uint64(), C.c_uint64()
+        self.lib.cg_tensor_map_cache_stats(C.byref(h), C.byref(m))
+        return {'hits': int(h.value), 'misses': int(m.value)}
 
     _tc_mode = 1
 
@@ -226,7 +242,7 @@ class CudaOps:
         self._chk(x, w, bias)
         g = self._geom(x.shape, w, stride, pad, ups)
         y = self.empty(g.G, g.B, g.Ho, g.Wo, g.Cout)
-        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 0))
+        ws = self._conv_ws(g, 0)
         self._timed('conv_fwd', g, lambda: self._ck(self.lib.cg_conv_fwd(
             C.byref(g), _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ws), ws.numel(), self._stream()), 'cg_conv_fwd'))
         return y
@@ -248,7 +264,7 @@ class CudaOps:
         g = self._geom((G,) + tuple(x_shape[1:]), w, stride, pad, ups)
         assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout), (tuple(dy.shape), (g.G, g.B, g.Ho, g.Wo, g.Cout))
         dx = self.empty(g.G, g.B, g.H, g.W, g.Cin)
-        ws = self._ws_for(self.lib.cg_conv_workspace_bytes(C.byref(g), 1))
+        ws = self._conv_ws(g, 1)
         self._timed('conv_dgrad', g, lambda: self._ck(self.lib.cg_conv_dgrad(
             C.byref(g), _p(dy), _p(w), _p(dx), _p(addend), _p(mask_src), mask_slope, _p(ws), ws.numel(), self._stream()),
             'cg_conv_dgrad'))
@@ -259,13 +275,13 @@ class CudaOps:
         self._chk(x, dy, dw, db)
         g = self._geom(x.shape, dw, stride, pad, ups)
         assert tuple(dy.shape) == (g.G, g.B, g.Ho, g.Wo, g.Cout)
-        need = self.lib.cg_conv_workspace_bytes(C.byref(g), 2)
         side = self._wgrad_stream
         if side is None:
-            ws = self._ws_for(need)
+            ws = self._conv_ws(g, 2)
             self._timed('conv_wgrad', g, lambda: self._ck(self.lib.cg_conv_wgrad(
                 C.byref(g), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), self._stream()), 'cg_conv_wgrad'))
             return
+        need = self.lib.cg_conv_workspace_bytes(C.byref(g), 2)
         side.wait_stream(torch.cuda.current_stream(self.device))  # x and dy were produced on the main stream
         with torch.cuda.stream(side):
             if self._ws_side is None or need > self._ws_side.numel():

@@ -419,6 +419,18 @@ def test_fused_losses(ops, ref):
     assert torch.equal(t1, t2)
 
 
+def test_tensor_map_cache(ops):
+    """TMA descriptors are cached by (pointer, geometry): the second identical launch encodes nothing."""
+    x = rnd(2, 2, 16, 16, 64, seed=1)
+    w = rnd(2, 64, 3, 3, 64, seed=2, scale=0.1)
+    y1 = ops.conv_fwd(x, w, None, 1, 1)
+    s1 = ops.tensor_map_cache_stats()
+    y2 = ops.conv_fwd(x, w, None, 1, 1)
+    s2 = ops.tensor_map_cache_stats()
+    assert torch.equal(y1, y2)
+    assert s2['hits'] > s1['hits'] and s2['misses'] == s1['misses']
+
+
 def test_adam(ops, ref):
     n = 100003
     p, g = rnd(n, seed=1), rnd(n, seed=2, scale=0.01)
