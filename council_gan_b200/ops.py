@@ -86,6 +86,8 @@ _SIGS = {
     'cg_gen_loss_bwd': (C.c_int, [C.POINTER(GenLossDesc), C.POINTER(GenLossHp), _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     'cg_loss_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'cg_zero': (C.c_int, [_fp, C.c_size_t, _fp]),
+    'cg_aug_color': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'cg_aug_resize_crop': (C.c_int, [_fp] * 5 + [C.c_int] * 7 + [_fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp, _fp]),
     'cg_adam_step': (C.c_int, [_fp, _fp, _fp, _fp, C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, _fp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -461,7 +463,7 @@ class CudaOps:
             ev.synchronize()  # the copy that last used this pinned buffer (8 updates ago) has long finished
         off, views = 0, []
         for a, sz in zip(arrays, sizes):
-            assert a.dtype in (torch.float32, torch.int32) and not a.is_cuda
+            assert a.dtype in (torch.float32, torch.int32) and not a.is_cuda, a.dtype
             n = a.numel() * 4
             host[off:off + n].view(a.dtype).copy_(a.reshape(-1))
             views.append(dev[off:off + n].view(a.dtype).view(a.shape))
@@ -602,6 +604,20 @@ class CudaOps:
                                           int(bool(accumulate)), _p(pub), _p(d_mask), _p(ws), ws.numel(), self._stream()),
                  'cg_gen_loss_bwd')
         return cl_douts, d_mask
+
+    # -- input pipeline (council_gan_b200/data.py) ------------------------------------------------------
+    def aug_color(self, pix, desc, opcode, param, B, max_pixels, any_contrast):
+        """one colour phase of the transform stack, in place on the packed uint8 batch (csrc/augment.cu)"""
+        lsum = torch.empty(B, dtype=torch.int64, device=self.device)
+        self._ck(self.lib.cg_aug_color(pix.data_ptr(), desc.data_ptr(), opcode.data_ptr(), param.data_ptr(), lsum.data_ptr(), B,
+                                       int(max_pixels), int(bool(any_contrast)), self._stream()), 'cg_aug_color')
+
+    def aug_resize_crop(self, pix, src_off, flip, slot, crop, n, H, W, oh, ow, ch, cw, bh, kh, ksh, bv, kv, ksv, out, nchw):
+        """flip + Pillow bilinear resize + crop + ToTensor + Normalize of n same-sized images into their batch slots"""
+        tmp = torch.empty(n * H * ow * 3, dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cg_aug_resize_crop(pix.data_ptr(), src_off.data_ptr(), flip.data_ptr(), slot.data_ptr(), crop.data_ptr(), n, H, W,
+                                             oh, ow, ch, cw, bh.data_ptr(), kh.data_ptr(), ksh, bv.data_ptr(), kv.data_ptr(), ksv,
+                                             tmp.data_ptr(), _p(out), _p(nchw), self._stream()), 'cg_aug_resize_crop')
 
     # -- optimiser --------------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

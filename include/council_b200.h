@@ -228,6 +228,24 @@ size_t cg_loss_workspace_bytes(int G, int B, int H, int W);
 /* plumbing: p[0:bytes] = 0 on `stream` (cudaMemsetAsync; keeps framework fill kernels out of the launch list) */
 int cg_zero(void* p, size_t bytes, void* stream);
 
+/* ---- input pipeline (the reference's per-image torchvision / Pillow transforms, utils.py:122-181, on a batch of decoded
+ *      uint8 RGB images in device memory; bit-exact with Pillow 12 / torchvision 0.26, see csrc/augment.cu) ------------------ */
+enum { CG_AUG_NONE = 0, CG_AUG_GRAY = 1, CG_AUG_BRIGHTNESS = 2, CG_AUG_CONTRAST = 3, CG_AUG_SATURATION = 4, CG_AUG_HUE = 5 };
+/* One colour phase, in place: image b (desc[b] = {byte offset into imgs, H, W, 0}, RGB interleaved) gets opcode[b] with param[b]:
+ * GRAY = RandomGrayscale; BRIGHTNESS / CONTRAST / SATURATION = ImageEnhance with factor param[b]; HUE = hue shift of
+ * (int)param[b] steps of 1/255 (pass float(int(hue_factor * 255))).  lsum: B x uint64 scratch.  transforms.ColorJitter applies its
+ * four ops in a random per-image order: call once per position of the permutation. */
+int cg_aug_color(uint8_t* imgs, const int32_t* desc, const int32_t* opcode, const float* param, unsigned long long* lsum,
+                 int B, int max_pixels, int any_contrast, void* stream);
+/* n images of ONE source size H x W (src_off[i] = byte offset): optional horizontal flip, Pillow bilinear resize to oh x ow
+ * (tables from Resample.c precompute_coeffs: bounds[out][2] = {first tap, count}, kk[out][ksize] 22-bit fixed point), crop window
+ * crop[i] = {top, left} of size ch x cw, ToTensor + Normalize(0.5, 0.5): image i is written to batch slot slot[i] of
+ * out_nhwc[.][ch][cw][4] (fp32, lane 3 = 0) and, if not NULL, of out_nchw[.][3][ch][cw].  tmp: n * H * ow * 3 bytes. */
+int cg_aug_resize_crop(const uint8_t* imgs, const int32_t* src_off, const int32_t* flip, const int32_t* slot,
+                       const int32_t* crop, int n, int H, int W, int oh, int ow, int ch, int cw, const int32_t* bounds_h,
+                       const int32_t* kk_h, int ksize_h, const int32_t* bounds_v, const int32_t* kk_v, int ksize_v,
+                       uint8_t* tmp, float* out_nhwc, float* out_nchw, void* stream);
+
 /* ---- optimiser (torch.optim.Adam as used at trainer_council.py:170-179) ----------------------- */
 int cg_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);

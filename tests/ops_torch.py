@@ -366,6 +366,46 @@ class TorchOps:
             d_mask = self.focus_bwd(mask, torch.tensor(coef, dtype=self.dtype, device=self.device), center, eps)
         return cl_douts, d_mask
 
+    # -- input pipeline: the numpy oracle stands in for csrc/augment.cu --------------------------------------
+    def aug_color(self, pix, desc, opcode, param, B, max_pixels, any_contrast):
+        import augment_oracle as ao
+        buf = pix.numpy()
+        for b in range(B):
+            off, h, w, _ = [int(v) for v in desc[b]]
+            img = buf[off:off + h * w * 3].reshape(h, w, 3)
+            op, f = int(opcode[b]), float(param[b])
+            if op == 1:
+                img[:] = ao.grayscale3(img)
+            elif op == 2:
+                img[:] = ao.adjust_brightness(img, f)
+            elif op == 3:
+                img[:] = ao.adjust_contrast(img, f)
+            elif op == 4:
+                img[:] = ao.adjust_saturation(img, f)
+            elif op == 5:
+                hsv = ao.rgb_to_hsv(img)
+                hsv[..., 0] = (hsv[..., 0].astype('int64') + int(f)) % 256
+                img[:] = ao.hsv_to_rgb(hsv)
+
+    def aug_resize_crop(self, pix, src_off, flip, slot, crop, n, H, W, oh, ow, ch, cw, bh, kh, ksh, bv, kv, ksv, out, nchw):
+        import numpy as np
+        import augment_oracle as ao
+        buf = pix.numpy()
+        for i in range(n):
+            off = int(src_off[i])
+            img = buf[off:off + H * W * 3].reshape(H, W, 3)
+            if int(flip[i]):
+                img = img[:, ::-1, :]
+            r = ao.resize_bilinear(np.ascontiguousarray(img), oh, ow)
+            ci, cj = int(crop[i][0]), int(crop[i][1])
+            x = r[ci:ci + ch, cj:cj + cw, :].astype(np.float32) / np.float32(255.0)
+            x = (x - np.float32(0.5)) / np.float32(0.5)
+            s_ = int(slot[i])
+            out[0, s_, :, :, :3] = torch.from_numpy(x).to(out.dtype)
+            out[0, s_, :, :, 3] = 0
+            if nchw is not None:
+                nchw[s_] = torch.from_numpy(x.transpose(2, 0, 1).copy()).to(nchw.dtype)
+
     # -- optimiser --------------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
         import math

@@ -1,0 +1,116 @@
+"""Input pipeline: the CPU oracle of the reference's per-image transforms (oracle/augment_oracle.py) must be
+bit-identical to torchvision + Pillow as installed (the libraries the reference's data loader calls, utils.py:122-181), and the
+product's parameter sampler / batch packing (council_gan_b200/data.py) must reproduce a seeded torchvision Compose exactly.
+CPU only; the CUDA kernels are checked against the same oracle in tests/test_augment_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+import augment_oracle as ao
+from common import config_for
+from council_gan_b200.data import DeviceAugment, precompute_coeffs
+from ops_torch import TorchOps
+
+PIL = pytest.importorskip('PIL.Image')
+T = pytest.importorskip('torchvision.transforms')
+TF = pytest.importorskip('torchvision.transforms.functional')
+
+
+def rnd_img(rng, h, w, smooth=False):
+    a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if smooth:
+        a = np.array(PIL.fromarray(a).resize((max(w // 4, 1), max(h // 4, 1))).resize((w, h), PIL.BICUBIC))
+    return a
+
+
+def test_colour_ops_bit_exact_vs_pillow():
+    rng = np.random.default_rng(0)
+    for smooth in (False, True):
+        img = rnd_img(rng, 109, 89, smooth)
+        pil = PIL.fromarray(img)
+        assert np.array_equal(ao.grayscale3(img), np.array(TF.rgb_to_grayscale(pil, 3)))
+        for f in (0.9, 1.1, 0.0, 1.0, 0.5, 1.7, 1.0321, 0.9993):
+            assert np.array_equal(ao.adjust_brightness(img, f), np.array(TF.adjust_brightness(pil, f))), ('brightness', f)
+            assert np.array_equal(ao.adjust_contrast(img, f), np.array(TF.adjust_contrast(pil, f))), ('contrast', f)
+            assert np.array_equal(ao.adjust_saturation(img, f), np.array(TF.adjust_saturation(pil, f))), ('saturation', f)
+        for f in (-0.1, 0.1, 0.05, -0.0371, 0.5, -0.5, 0.0):
+            assert np.array_equal(ao.adjust_hue(img, f), np.array(TF.adjust_hue(pil, f))), ('hue', f)
+
+
+def test_hsv_conversion_bit_exact_on_a_colour_lattice():
+    """every 3rd value of each channel (614 k colours) through Pillow's float RGB<->HSV code, both directions"""
+    v = np.arange(0, 256, 3)
+    r, g, b = np.meshgrid(v, v, v, indexing='ij')
+    allc = np.stack([r, g, b], -1).astype(np.uint8).reshape(len(v), -1, 3)
+    assert np.array_equal(ao.rgb_to_hsv(allc), np.array(PIL.fromarray(allc).convert('HSV')))
+    assert np.array_equal(ao.hsv_to_rgb(allc), np.array(PIL.fromarray(allc, 'HSV').convert('RGB')))
+
+
+@pytest.mark.parametrize('h,w,size', [(218, 178, 256), (218, 178, 128), (300, 400, 256), (64, 48, 128), (500, 375, 128), (256, 256, 256),
+                                      (178, 218, 256)])
+def test_resize_bit_exact_vs_pillow(h, w, size):
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rnd_img(rng, h, w, True)
+    oh, ow = ao.resized_size(h, w, size)
+    want = np.array(TF.resize(PIL.fromarray(img), size))
+    assert want.shape == (oh, ow, 3)
+    assert np.array_equal(ao.resize_bilinear(img, oh, ow), want)
+    b1, k1 = precompute_coeffs(w, ow)   # the product's table builder == the oracle's
+    b2, k2 = ao.precompute_coeffs(w, ow)
+    assert np.array_equal(b1, b2) and np.array_equal(k1, k2)
+
+
+def reference_compose(hp, is_data_A, train, new_size, height, width):
+    """The torchvision Compose get_data_loader_folder builds (utils.py:122-176) for the flags of the shipped configs."""
+    tl = [T.ToTensor(), T.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    if not train:
+        tl = [T.CenterCrop(new_size)] + tl
+    tl = [T.RandomCrop((height, width))] + tl
+    tl = [T.Resize(new_size)] + tl
+    if hp['do_HorizontalFlip'] and train:
+        tl = [T.RandomHorizontalFlip()] + tl
+    jit = hp['do_ColorJitter_A'] if is_data_A else hp['do_ColorJitter_B']
+    if jit and train:
+        tl = [T.ColorJitter(brightness=hp['ColorJitter_brightness'], contrast=hp['ColorJitter_contrast'],
+                            saturation=hp['ColorJitter_saturation'], hue=hp['ColorJitter_hue'])] + tl
+    if hp['do_RandomGrayscale'] and train:
+        tl = [T.RandomGrayscale(p=hp['RandomGrayscale_P'])] + tl
+    return T.Compose(tl)
+
+
+AUG = {'do_HorizontalFlip': True, 'do_VerticalFlip': False, 'do_ColorJitter_A': True, 'do_ColorJitter_B': True, 'ColorJitter_hue': 0.1,
+       'ColorJitter_brightness': 0.1, 'ColorJitter_saturation': 0.1, 'ColorJitter_contrast': 0.1, 'do_RandomGrayscale': True,
+       'RandomGrayscale_P': 0.3, 'do_RandomRotation': False, 'do_RandomAffine': False, 'do_RandomPerspective': False,
+       'do_RandomResizedCrop': False}   # configs/male2female_council_folder.yaml:96-117 (grayscale probability raised to exercise it)
+
+
+@pytest.mark.parametrize('train', [True, False])
+def test_whole_pipeline_equals_seeded_torchvision_compose(train):
+    """Same torch seed -> same random parameters (same calls in the same order) -> bit-identical tensors, image after image, through
+    the product's DeviceAugment (host packing / grouping / phases) with the oracle standing in for the CUDA kernels."""
+    hp = dict(config_for('male2female'), **AUG)
+    hp['new_size'], hp['crop_image_height'], hp['crop_image_width'] = 64, 48, 56
+    rng = np.random.default_rng(5)
+    imgs = [rnd_img(rng, 109, 89, True), rnd_img(rng, 70, 120, True), rnd_img(rng, 109, 89, True), rnd_img(rng, 64, 64, True)]
+    new_size = hp['new_size']
+    ch, cw = (hp['crop_image_height'], hp['crop_image_width']) if train else (new_size, new_size)
+    comp = reference_compose(hp, True, train, new_size, ch, cw)
+    torch.manual_seed(1234)
+    want = [comp(PIL.fromarray(im)) for im in imgs]
+    aug = DeviceAugment(TorchOps('cpu'), hp, is_data_A=True, train=train)
+    torch.manual_seed(1234)
+    params = [aug.sample(im.shape[0], im.shape[1]) for im in imgs]
+    for im, p, w in zip(imgs, params, want):  # oracle, image by image
+        got = ao.train_transform(im, p, new_size, ch, cw)
+        assert np.array_equal(got, w.numpy()), 'oracle pipeline differs from torchvision'
+    out, nchw = aug(imgs, params=params, want_nchw=True)  # product host logic, whole (ragged) batch
+    for b, w in enumerate(want):
+        assert torch.equal(nchw[b], w)
+        assert torch.equal(out[0, b, :, :, :3].permute(2, 0, 1), w) and float(out[0, b, :, :, 3].abs().max()) == 0
+
+
+def test_unsupported_transforms_raise():
+    hp = dict(config_for('male2female'), **AUG)
+    for k in ('do_VerticalFlip', 'do_RandomRotation', 'do_RandomAffine', 'do_RandomPerspective', 'do_RandomResizedCrop'):
+        with pytest.raises(NotImplementedError):
+            DeviceAugment(TorchOps('cpu'), dict(hp, **{k: True}), True, True)
