@@ -220,7 +220,7 @@ class DeviceFolderLoader:
     def _decode(path):
         from PIL import Image
         with open(path, 'rb') as f:
-            return np.asarray(Image.open(f).convert('RGB'))  # data.py default_loader
+            return np.array(Image.open(f).convert('RGB'))  # data.py default_loader (a writable copy)
 
     def __iter__(self):
         order = torch.randperm(len(self.files)).tolist() if self.train else list(range(len(self.files)))

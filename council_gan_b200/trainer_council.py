@@ -238,6 +238,10 @@ class Council_Trainer(nn.Module):
     def _img(self, x):
         """NCHW image batch (any device) -> shared channels-last [1,B,H,W,4] on the device.  Cached per tensor OBJECT (the
         three updates of one iteration receive the same tensors, train.py:241-250); a new tensor is always uploaded."""
+        if x.dim() == 5:  # already the step's layout: a DeviceAugment / DeviceFolderLoader batch (data.py)
+            if x.shape[0] != 1 or x.shape[-1] != IMG_C or x.device.type != torch.device(self.ops.device).type or x.dtype != self.ops.dtype:
+                raise ValueError('channels-last image batches must be [1, B, H, W, %d] %s tensors on %s' % (IMG_C, self.ops.dtype, self.ops.device))
+            return x
         key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
         for slot in ('k', 'k2'):
             hit = self._img_cache.get(slot)
@@ -249,6 +253,10 @@ class Council_Trainer(nn.Module):
         self._img_cache['k2'] = self._img_cache.get('k')
         self._img_cache['k'] = (key, img, x)
         return img
+
+    @staticmethod
+    def _bsz(x):
+        return x.shape[1] if x.dim() == 5 else x.size(0)
 
     def _noise(self, batch):
         """torch.randn(B, style_dim, 1, 1) on the CPU generator (:284-285,741,744,807,809) as a HOST tensor [1,B,1,1,S];
@@ -356,9 +364,9 @@ class Council_Trainer(nn.Module):
         img_a, img_b = self._img(x_a), self._img(x_b)
         noise = []
         if self.do_a2b_conf:  # :740-745
-            noise.append(('a2b', self._noise(x_b.size(0))))
+            noise.append(('a2b', self._noise(self._bsz(x_b))))
         if self.do_b2a_conf:
-            noise.append(('b2a', self._noise(x_a.size(0))))
+            noise.append(('b2a', self._noise(self._bsz(x_a))))
         s = dict(zip((k for k, _ in noise), ops.stage([v for _, v in noise])))
         total = ops.empty(N)
         inv_world = 1.0 / self.world
@@ -404,9 +412,9 @@ class Council_Trainer(nn.Module):
         img_a, img_b = self._img(x_a), self._img(x_b)
         noise = []
         if self.do_b2a_conf:  # :806-809: s_a first, then s_b
-            noise.append(('b2a', self._noise(x_a.size(0))))
+            noise.append(('b2a', self._noise(self._bsz(x_a))))
         if self.do_a2b_conf:
-            noise.append(('a2b', self._noise(x_b.size(0))))
+            noise.append(('a2b', self._noise(self._bsz(x_b))))
         less = cc['discriminetro_less_style_by']
         # peers: python `random`, without replacement, pool refilled when exhausted (:861-868)
         Kcfg = cc['numberOfCouncil_dis_relative_iteration']
@@ -478,8 +486,8 @@ class Council_Trainer(nn.Module):
         ops, N = self.ops, self.council_size
         fl = hp['focus_loss']
         img_a, img_b = self._img(x_a), self._img(x_b)
-        s_a = self._noise(x_a.size(0))  # :284-285 both are always drawn, a first
-        s_b = self._noise(x_b.size(0))
+        s_a = self._noise(self._bsz(x_a))  # :284-285 both are always drawn, a first
+        s_b = self._noise(self._bsz(x_b))
         s_a, s_b = ops.stage([s_a, s_b])
         s = {'a2b': s_b, 'b2a': s_a}
         it = hp['iteration']
@@ -616,6 +624,8 @@ class Council_Trainer(nn.Module):
                 res[d] = (None, None, None, None)
                 continue
             x = x_a if d == 'a2b' else x_b
+            if x.dim() == 5:
+                raise ValueError('sample() takes NCHW images like the reference (trainer_council.py:643)')
             B = x.size(0)
             fixed = (self.s_b if s_b is None else s_b) if d == 'a2b' else (self.s_a if s_a is None else s_a)
             s2 = torch.randn(B, self.style_dim, 1, 1)  # :649 / :655

@@ -11,7 +11,7 @@ the three shipped configurations (`configs/*_council_folder.yaml:92-119`):
 The arithmetic lives in third-party code that is not under /root/reference: torchvision (pinned by the reference's
 conda_requirements.yml as torchvision=0.6.0; 0.26.0 in this image) and Pillow (7.1; 12.2.0 here).  Pinning: the
 functions below are checked bit-for-bit against torchvision + Pillow as installed here
-(tests/test_augment_oracle_cpu.py), on random images and on every parameter combination the configs can draw.
+(tests/test_augment_cpu.py), on random images and on every parameter combination the configs can draw.
 
 Integer formulas restated from Pillow's C sources (libImaging): Convert.c rgb2l / rgb2hsv / hsv2rgb, Blend.c, Resample.c
 (precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc, PRECISION_BITS = 32 - 8 - 2).

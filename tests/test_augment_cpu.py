@@ -114,3 +114,42 @@ def test_unsupported_transforms_raise():
     for k in ('do_VerticalFlip', 'do_RandomRotation', 'do_RandomAffine', 'do_RandomPerspective', 'do_RandomResizedCrop'):
         with pytest.raises(NotImplementedError):
             DeviceAugment(TorchOps('cpu'), dict(hp, **{k: True}), True, True)
+
+
+def test_trainer_takes_the_device_batches_as_they_are(tmp_path):
+    """folder -> DeviceFolderLoader -> Council_Trainer.dis_update: the channels-last batch goes into the step without a layout pass and
+    gives the same losses as the NCHW tensor of the reference API."""
+    import council_oracle as co
+    from common import load_golden, setup_case
+    from council_gan_b200.data import DeviceFolderLoader
+    from council_gan_b200.trainer_council import Council_Trainer
+    from test_trainer_host_cpu import load_states
+    gold = load_golden('glasses64_n2_b2_early')
+    hp, states, _, _ = setup_case(gold)
+    hp = dict(hp, **AUG)
+    hp['new_size'], hp['crop_image_height'], hp['crop_image_width'] = 64, 64, 64
+    rng = np.random.default_rng(1)
+    for dom in ('trainA', 'trainB'):
+        (tmp_path / dom).mkdir()
+        for k in range(4):
+            PIL.fromarray(rnd_img(rng, 80, 72, True)).save(str(tmp_path / dom / ('%d.png' % k)))
+    ops = TorchOps('cpu')
+    losses = []
+    for want_nchw in (False, True):
+        torch.manual_seed(3)
+        la = DeviceFolderLoader(ops, str(tmp_path / 'trainA'), 2, True, hp, True, num_workers=2, want_nchw=want_nchw)
+        lb = DeviceFolderLoader(ops, str(tmp_path / 'trainB'), 2, True, hp, False, num_workers=2, want_nchw=want_nchw)
+        assert len(la) == 2
+        ba, bb = next(iter(la)), next(iter(lb))
+        if want_nchw:
+            (ca, ba), (cb, bb) = ba, bb
+            assert ba.shape == (2, 3, 64, 64) and ca.shape == (1, 2, 64, 64, 4)
+        co.seed_all(3)
+        tr = Council_Trainer(hp, 'cpu', _ops=ops)
+        load_states(tr, states)
+        co.seed_all(7)
+        tr.dis_update(ba, bb, hp)
+        tr.gen_update(ba, bb, hp, hp['iteration'])
+        losses.append([float(v) for v in tr.loss_dis_total_s] + [float(v) for v in tr.loss_gen_total_s])
+        assert tr.img_cache_misses == (2 if want_nchw else 0)
+    assert losses[0] == losses[1]
