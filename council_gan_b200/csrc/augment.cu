@@ -8,54 +8,9 @@
 //   * bilinear resize = separable triangle filter in 22-bit fixed point, uint8 between the passes (Resample.c)
 // The output is written directly in the layout the training step consumes: channels-last fp32 [B][H][W][4], values in [-1, 1].
 #include "common.cuh"
+#include "augment_math.cuh"
 
 namespace cg {
-
-__device__ __forceinline__ int lum(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
-
-// Image.blend for one channel: never let the compiler contract the multiply-add (Pillow's C code is not built with FMA)
-__device__ __forceinline__ int blend1(int in1, int in2, float a, bool interp) {
-    float temp = __fadd_rn((float)in1, __fmul_rn(a, (float)(in2 - in1)));
-    if (interp) return (int)temp;
-    return temp <= 0.f ? 0 : (temp >= 255.f ? 255 : (int)temp);
-}
-
-__device__ __forceinline__ void rgb2hsv(int r, int g, int b, int& uh, int& us, int& uv) {
-    int maxc = max(r, max(g, b)), minc = min(r, min(g, b));
-    uv = maxc;
-    if (minc == maxc) { uh = 0; us = 0; return; }
-    float cr = (float)(maxc - minc);
-    float s = __fdiv_rn(cr, (float)maxc);
-    float rc = __fdiv_rn((float)(maxc - r), cr), gc = __fdiv_rn((float)(maxc - g), cr), bc = __fdiv_rn((float)(maxc - b), cr);
-    float h;
-    if (r == maxc) h = __fsub_rn(bc, gc);
-    else if (g == maxc) h = (float)(2.0 + (double)rc - (double)bc);
-    else h = (float)(4.0 + (double)gc - (double)rc);
-    h = (float)fmod((double)h / 6.0 + 1.0, 1.0);
-    int ih = (int)((double)h * 255.0), is = (int)((double)s * 255.0);
-    uh = min(max(ih, 0), 255);
-    us = min(max(is, 0), 255);
-}
-__device__ __forceinline__ int round8(float x) { return min(max((int)floor((double)x + 0.5), 0), 255); }
-__device__ __forceinline__ void hsv2rgb(int h, int s, int v, int& r, int& g, int& b) {
-    if (s == 0) { r = g = b = v; return; }
-    float fh = __fdiv_rn(__fmul_rn((float)h, 6.0f), 255.0f);
-    float fs = __fdiv_rn((float)s, 255.0f);
-    int i = (int)floorf(fh);
-    float f = __fsub_rn(fh, (float)i);
-    float vv = (float)v;
-    int p = round8(__fmul_rn(vv, __fsub_rn(1.0f, fs)));
-    int q = round8(__fmul_rn(vv, __fsub_rn(1.0f, __fmul_rn(fs, f))));
-    int t = round8(__fmul_rn(vv, __fsub_rn(1.0f, __fmul_rn(fs, __fsub_rn(1.0f, f)))));
-    switch (i % 6) {
-        case 0: r = v; g = t; b = p; break;
-        case 1: r = q; g = v; b = p; break;
-        case 2: r = p; g = v; b = t; break;
-        case 3: r = p; g = q; b = v; break;
-        case 4: r = t; g = p; b = v; break;
-        default: r = v; g = p; b = q; break;
-    }
-}
 
 // per-image L sums (exact integers: order-independent atomics) for the images whose current op is the contrast adjustment
 __global__ void __launch_bounds__(256) aug_lsum_kernel(const uint8_t* __restrict__ imgs, const int32_t* __restrict__ desc,
@@ -80,37 +35,15 @@ __global__ void __launch_bounds__(256) aug_color_kernel(uint8_t* __restrict__ im
     const int npix = desc[b * 4 + 1] * desc[b * 4 + 2];
     uint8_t* p = imgs + desc[b * 4];
     const float f = param[b];
-    const bool interp = f >= 0.f && f <= 1.f;
-    int mean = 0;
-    if (op == CG_AUG_CONTRAST) mean = (int)((double)lsum[b] / (double)npix + 0.5);  // int(ImageStat.Stat(L).mean[0] + 0.5)
-    const int hshift = op == CG_AUG_HUE ? (int)(f * 255.f) : 0;                     // np.int32(hue_factor * 255): truncation
+    const int mean = op == CG_AUG_CONTRAST ? contrast_mean(lsum[b], npix) : 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         int r = p[3 * i], g = p[3 * i + 1], bb = p[3 * i + 2];
-        if (op == CG_AUG_GRAY) {
-            r = g = bb = lum(r, g, bb);
-        } else if (op == CG_AUG_BRIGHTNESS) {
-            if (f != 1.f) { r = f == 0.f ? 0 : blend1(0, r, f, interp); g = f == 0.f ? 0 : blend1(0, g, f, interp); bb = f == 0.f ? 0 : blend1(0, bb, f, interp); }
-        } else if (op == CG_AUG_CONTRAST) {
-            if (f != 1.f) { r = f == 0.f ? mean : blend1(mean, r, f, interp); g = f == 0.f ? mean : blend1(mean, g, f, interp); bb = f == 0.f ? mean : blend1(mean, bb, f, interp); }
-        } else if (op == CG_AUG_SATURATION) {
-            const int l = lum(r, g, bb);
-            if (f != 1.f) { r = f == 0.f ? l : blend1(l, r, f, interp); g = f == 0.f ? l : blend1(l, g, f, interp); bb = f == 0.f ? l : blend1(l, bb, f, interp); }
-        } else if (op == CG_AUG_HUE) {
-            int h, s, v;
-            rgb2hsv(r, g, bb, h, s, v);
-            h = (h + hshift) & 255;  // uint8 wrap-around
-            hsv2rgb(h, s, v, r, g, bb);
-        }
+        color_px(op, f, mean, r, g, bb);
         p[3 * i] = (uint8_t)r; p[3 * i + 1] = (uint8_t)g; p[3 * i + 2] = (uint8_t)bb;
     }
 }
 
 // ---- Pillow's two-pass resize for n images of one source size -----------------------------------------------------------------
-constexpr int RS_BITS = 32 - 8 - 2;
-__device__ __forceinline__ uint8_t rs_clip8(long long v) {
-    long long r = v >> RS_BITS;
-    return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
-}
 // horizontal pass (+ optional mirror of the source columns: RandomHorizontalFlip precedes Resize): tmp[n][H][ow][3]
 __global__ void __launch_bounds__(256) aug_resize_h_kernel(const uint8_t* __restrict__ imgs, const int32_t* __restrict__ src_off,
                                                            const int32_t* __restrict__ flip, uint8_t* __restrict__ tmp,
@@ -123,15 +56,7 @@ __global__ void __launch_bounds__(256) aug_resize_h_kernel(const uint8_t* __rest
     uint8_t* dst = tmp + (long)n * total * 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int y = i / ow, xx = i - y * ow;
-        const int x0 = bounds[2 * xx], cnt = bounds[2 * xx + 1];
-        long long a0 = 1ll << (RS_BITS - 1), a1 = a0, a2 = a0;
-        for (int x = 0; x < cnt; x++) {
-            const int sx = fl ? W - 1 - (x0 + x) : x0 + x;
-            const uint8_t* px = src + ((long)y * W + sx) * 3;
-            const long long k = kk[xx * ksize + x];
-            a0 += px[0] * k; a1 += px[1] * k; a2 += px[2] * k;
-        }
-        dst[3 * i] = rs_clip8(a0); dst[3 * i + 1] = rs_clip8(a1); dst[3 * i + 2] = rs_clip8(a2);
+        resize_h_px(src + (long)y * W * 3, W, fl, bounds, kk, ksize, xx, dst + 3 * (long)i);
     }
 }
 // vertical pass fused with RandomCrop / CenterCrop, ToTensor (x / 255) and Normalize((x - 0.5) / 0.5): only the cropped window of the
@@ -147,17 +72,8 @@ __global__ void __launch_bounds__(256) aug_resize_v_crop_kernel(const uint8_t* _
     const long sl = slot[n];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int y = i / cw, x = i - y * cw;
-        const int yy = ci + y, xx = cj + x;
-        const int y0 = bounds[2 * yy], cnt = bounds[2 * yy + 1];
-        long long a0 = 1ll << (RS_BITS - 1), a1 = a0, a2 = a0;
-        for (int t = 0; t < cnt; t++) {
-            const uint8_t* px = src + ((long)(y0 + t) * ow + xx) * 3;
-            const long long k = kk[yy * ksize + t];
-            a0 += px[0] * k; a1 += px[1] * k; a2 += px[2] * k;
-        }
-        float v[3] = {(float)rs_clip8(a0), (float)rs_clip8(a1), (float)rs_clip8(a2)};
-#pragma unroll
-        for (int c = 0; c < 3; c++) v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn(v[c], 255.0f), 0.5f), 0.5f);
+        float v[3];
+        resize_v_px(src, ow, bounds, kk, ksize, ci + y, cj + x, v);
         reinterpret_cast<float4*>(out_nhwc)[sl * total + i] = make_float4(v[0], v[1], v[2], 0.f);
         if (out_nchw) {
             float* o = out_nchw + sl * 3 * total + i;

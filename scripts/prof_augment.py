@@ -7,6 +7,7 @@ import time
 import numpy as np
 import torch
 
+sys.path.insert(0, '.')
 sys.path.insert(0, 'tests')
 sys.path.insert(0, 'oracle')
 from common import config_for  # noqa: E402

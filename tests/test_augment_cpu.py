@@ -153,3 +153,77 @@ def test_trainer_takes_the_device_batches_as_they_are(tmp_path):
         losses.append([float(v) for v in tr.loss_dis_total_s] + [float(v) for v in tr.loss_gen_total_s])
         assert tr.img_cache_misses == (2 if want_nchw else 0)
     assert losses[0] == losses[1]
+
+
+# ---- the kernels' own arithmetic, compiled for the host ---------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def hostlib(tmp_path_factory):
+    """g++ build of csrc/augment_math.cuh (the per-pixel functions the CUDA kernels call) behind the C ABI's argument lists"""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path_factory.mktemp('aughost') / 'libaughost.so')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-o', so, os.path.join(here, 'augment_host.cpp')])
+    return ctypes.CDLL(so)
+
+
+class HostKernelOps(TorchOps):
+    """TorchOps with the two input-pipeline ops running the kernels' arithmetic (host build) instead of the numpy oracle"""
+
+    def __init__(self, lib):
+        super().__init__('cpu')
+        self.lib = lib
+
+    def aug_color(self, pix, desc, opcode, param, B, max_pixels, any_contrast):
+        assert self.lib.h_aug_color(pix.data_ptr(), desc.data_ptr(), opcode.data_ptr(), param.data_ptr(), B) == 0
+
+    def aug_resize_crop(self, pix, src_off, flip, slot, crop, n, H, W, oh, ow, ch, cw, bh, kh, ksh, bv, kv, ksv, out, nchw):
+        import ctypes
+        tmp = torch.empty(n * H * ow * 3, dtype=torch.uint8)
+        P = ctypes.c_void_p
+        args = [P(t.data_ptr()) for t in (pix, src_off, flip, slot, crop)] + [n, H, W, oh, ow, ch, cw, P(bh.data_ptr()), P(kh.data_ptr()), ksh,
+                                                                             P(bv.data_ptr()), P(kv.data_ptr()), ksv, P(tmp.data_ptr()),
+                                                                             P(out.data_ptr()), P(nchw.data_ptr() if nchw is not None else None)]
+        assert self.lib.h_aug_resize_crop(*args) == 0
+
+
+def test_kernel_hue_arithmetic_every_colour(hostlib):
+    """all 2^24 colours through the kernels' RGB -> HSV -> shift -> RGB code (host build) == the oracle (== Pillow)"""
+    import ctypes
+    v = np.arange(256, dtype=np.uint8)
+    for shift in (0, -14, 25, 127, -128):
+        for r0 in range(0, 256, 32):
+            r, g, b = np.meshgrid(v[r0:r0 + 32], v, v, indexing='ij')
+            rgb = np.ascontiguousarray(np.stack([r, g, b], -1).reshape(-1, 3))
+            out = np.empty_like(rgb)
+            hostlib.h_hue_all(ctypes.c_void_p(rgb.ctypes.data), ctypes.c_void_p(out.ctypes.data), ctypes.c_long(rgb.shape[0]), shift)
+            hsv = ao.rgb_to_hsv(rgb[None])
+            hsv[..., 0] = (hsv[..., 0].astype(np.int64) + shift) % 256
+            assert np.array_equal(out, ao.hsv_to_rgb(hsv)[0]), (shift, r0)
+
+
+@pytest.mark.parametrize('train', [True, False])
+def test_kernel_arithmetic_whole_pipeline_on_host(hostlib, train):
+    """DeviceAugment driving the kernels' arithmetic (host build): bit-identical to the oracle on ragged batches, every jitter order,
+    interpolating and extrapolating factors -- what tests/test_augment_gpu.py checks on the GPU, minus the grid indexing"""
+    import itertools
+    hp = dict(config_for('male2female'), **AUG)
+    hp['new_size'], hp['crop_image_height'], hp['crop_image_width'] = 96, 80, 88
+    rng = np.random.default_rng(11)
+    orders = list(itertools.permutations(range(4)))
+    sizes = [(109, 89), (120, 160), (96, 96)] * 8
+    imgs = [rnd_img(rng, h, w, k % 2 == 0) for k, (h, w) in enumerate(sizes)]
+    aug = DeviceAugment(HostKernelOps(hostlib), hp, is_data_A=True, train=train)
+    ch, cw = (80, 88) if train else (96, 96)
+    torch.manual_seed(2)
+    params = [aug.sample(h, w) for h, w in sizes]
+    if train:
+        for k, (p, o) in enumerate(zip(params, orders)):
+            p['gray'] = k % 5 == 0
+            p['jitter'] = (list(o), 0.6 + 0.07 * k, 1.9 - 0.06 * k, 0.0 if k == 3 else (1.0 if k == 4 else 0.4 + 0.1 * k), -0.5 + k / 23.0)
+    out, nchw = aug(imgs, params=params, want_nchw=True)
+    for b, (im, p) in enumerate(zip(imgs, params)):
+        want = torch.from_numpy(ao.train_transform(im, p, 96, ch, cw))
+        assert torch.equal(nchw[b], want), (b, p, float((nchw[b] - want).abs().max()))
+        assert torch.equal(out[0, b, :, :, :3].permute(2, 0, 1), want)
