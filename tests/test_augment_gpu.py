@@ -56,7 +56,7 @@ def test_every_jitter_order_and_extreme_factors():
     aug = DeviceAugment(ops, hp, is_data_A=True, train=True)
     params = []
     for k, o in enumerate(orders):
-        params.append({'gray': k % 5 == 0, 'flip': k % 2 == 1, 'crop': (k % 7, k % 3),
+        params.append({'gray': k % 5 == 0, 'flip': k % 2 == 1, 'crop': (k % 8, 0),  # 80 x 72 -> 71 x 64: rows 0..7, column 0
                        'jitter': (list(o), 0.6 + 0.07 * k, 1.9 - 0.06 * k, 0.0 if k == 3 else 0.4 + 0.1 * k, -0.5 + k / 23.0)})
     _, nchw = aug(imgs, params=params, want_nchw=True)
     for b, (im, p) in enumerate(zip(imgs, params)):
