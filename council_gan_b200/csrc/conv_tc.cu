@@ -58,6 +58,7 @@ thread_local int g_pair_cap = 0;
 thread_local int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
 thread_local int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
 thread_local int g_wgrad_xm2 = 1;   // ... also for the x-on-M kernel
+thread_local int g_epi_coalesce = 1;  // epilogue stores through the per-warp patch (full sectors); bit 20 of the mode clears it
 thread_local int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
 thread_local int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
                       // bit 3: weight gradient (MN-major operands: measured 15-20 % slower than single CTAs: off)  // cta_group::2 kernels for 256-wide layers (cg_set_tensor_core_mode bit 8 clears it for A/B runs)
@@ -171,7 +172,52 @@ struct TcParams {
     long stats_gbc;                 // G*B*Cout
     int act; float slope;
     int stages;
+    int coalesce;                   // epilogue leaves through the per-warp shared-memory patch with full-sector global accesses
 };
+
+// Epilogue store of one 32-row x 32-column accumulator block (lane = pixel row, v = its 32 channels, bias already added) with
+// FULL-sector global accesses.  In the accumulator layout a warp-wide float4 store touches 32 different pixels, 16 bytes each:
+// 32 half-written sectors per instruction, which capped the store-heavy layers near 2 TB/s (profiles/r02_summary.md).  Here the
+// block goes through a 2 KB per-warp shared-memory patch, 16 columns at a time (64-byte rows, float4 index XOR-swizzled by
+// (row >> 1) & 3: conflict-free for the row-wise writes and for the reads below), after which four consecutive lanes own 64
+// contiguous bytes of one pixel -- for the stores and for the residual (addend) / activation-mask loads of the data gradient alike.
+// out_off: element offset of this lane's pixel row at the block's first column, or -1 when the row is not stored.
+__device__ __forceinline__ void epilogue_store_coalesced(const float (&v)[32], float4* patch, int lane, long out_off, float* __restrict__ y,
+                                                         const float* __restrict__ addend, const float* __restrict__ mask_src, int act,
+                                                         float slope) {
+    const int wsw = (lane >> 1) & 3;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            patch[lane * 4 + (j ^ wsw)] = make_float4(v[16 * half + 4 * j], v[16 * half + 4 * j + 1], v[16 * half + 4 * j + 2], v[16 * half + 4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = i * 8 + (lane >> 2), c4 = lane & 3;
+            float4 o = patch[r * 4 + (c4 ^ ((r >> 1) & 3))];
+            const long off = __shfl_sync(0xffffffffu, out_off, r);
+            if (off < 0) continue;
+            const long e = off + half * 16 + c4 * 4;
+            if (addend) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(addend + e));
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            if (mask_src) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(mask_src + e));
+                o.x *= a.x > 0.f ? 1.f : slope; o.y *= a.y > 0.f ? 1.f : slope;
+                o.z *= a.z > 0.f ? 1.f : slope; o.w *= a.w > 0.f ? 1.f : slope;
+            } else if (act == CG_ACT_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            } else if (act == CG_ACT_LRELU) {
+                o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+                o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+            }
+            *reinterpret_cast<float4*>(y + e) = o;
+        }
+    }
+}
 
 template <int BK>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -188,6 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // 4 x (32 x 36) floats, only carved when p.stats
+    float4* store_patch = reinterpret_cast<float4*>(stat_smem + (p.stats ? 4 * 32 * 36 : 0));  // 4 x 2 KB, only carved when p.coalesce
 
     const int MT = (p.B * p.P * p.Q + TC_BM - 1) / TC_BM;  // pixel tiles per (group, class)
     const int NT = (p.Cout + p.bn - 1) / p.bn;
@@ -380,6 +427,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
                     const long col = (long)(g * p.B + img) * p.Cout + nt * p.bn + c0 + lane;
                     *reinterpret_cast<float2*>(p.stats + ((long)chunk * p.stats_gbc + col) * 2) = make_float2(cs, cq);
                 }
+                if (p.coalesce) {
+                    if (p.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 a = __ldg(bp + j);
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        }
+                    }
+                    epilogue_store_coalesced(v, store_patch + quad * 128, lane, valid ? out_off + c0 : -1, p.y, p.addend, p.mask_src, p.act, p.slope);
+                } else
                 if (valid) {
                     if (p.bias) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
@@ -507,6 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // 4 x (32 x 36) floats, only carved when p.stats
+    float4* store_patch = reinterpret_cast<float4*>(stat_smem + (p.stats ? 4 * 32 * 36 : 0));  // 4 x 2 KB, only carved when p.coalesce
 
     const int pq = p.P * p.Q;
     const int PT = (p.B * pq + 2 * TC_BM - 1) / (2 * TC_BM);  // pair tiles (256 pixels) per (group, class)
@@ -668,6 +727,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     const long col = (long)(g * p.B + img) * p.Cout + nt * p.bn + c0 + lane;
                     if (mt * TC_BM < p.B * pq) *reinterpret_cast<float2*>(p.stats + ((long)chunk * p.stats_gbc + col) * 2) = make_float2(cs, cq);
                 }
+                if (p.coalesce) {
+                    if (p.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 a = __ldg(bp + j);
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        }
+                    }
+                    epilogue_store_coalesced(v, store_patch + quad * 128, lane, valid ? out_off + c0 : -1, p.y, p.addend, p.mask_src, p.act, p.slope);
+                } else
                 if (valid) {
                     if (p.bias) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)g * p.Cout + nt * p.bn + c0);
@@ -817,10 +887,11 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     while (cps > 1 && (cps > kiters || cps * chunk_bytes > 64 * 1024)) cps >>= 1;
     p.cps = cps;
     int stage_bytes = cps * chunk_bytes;
-    const int stat_bytes = p.stats ? 4 * 32 * 36 * 4 : 0;
+    p.coalesce = g_epi_coalesce && p.bn >= 32 && p.act != CG_ACT_TANH ? 1 : 0;
+    const int stat_bytes = (p.stats ? 4 * 32 * 36 * 4 : 0) + (p.coalesce ? 4 * 2048 : 0);
     // narrow tiles are bound by the single MMA-issuing thread's per-stage latency: two co-resident CTAs per SM interleave their MMAs
     const bool two = g_fwd_2cta && p.bn <= 64 && !p.stats && 2 * stage_bytes <= 100 * 1024;
-    int stages = ((two ? 104 : 226) * 1024 - 1024 - 512 - stat_bytes) / stage_bytes;  // 227 KB dynamic shared memory per SM
+    int stages = ((two ? 112 : 226) * 1024 - 1024 - 512 - stat_bytes) / stage_bytes;  // two co-resident CTAs: 2 x (112 KB + 1 KB reserved) <= 228 KB  // 227 KB dynamic shared memory per SM
     if (stages > 12) stages = 12;
     if (stages > 4 && stage_bytes >= 48 * 1024) stages = 4;
     if (p.n_store == 0) p.n_store = p.bn;

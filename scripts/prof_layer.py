@@ -9,6 +9,8 @@ kind = sys.argv[1]
 G, B, H, W, Cin, Cout, K, stride, pad = [int(v) for v in sys.argv[2:11]]
 iters = int(sys.argv[11]) if len(sys.argv) > 11 else 5
 ops = CudaOps('cuda:0')
+if os.environ.get('COUNCIL_TC_MODE'):
+    ops.set_tensor_core_mode(int(os.environ['COUNCIL_TC_MODE'], 0))
 g = torch.Generator().manual_seed(0)
 x = torch.randn(G, B, H, W, Cin, generator=g).cuda()
 w = (torch.randn(G, Cout, K, K, Cin, generator=g) * 0.05).cuda()
@@ -34,4 +36,4 @@ for k in (['fwd', 'dgrad', 'wgrad'] if kind == 'all' else [kind]):
         run(k)
     e1.record()
     torch.cuda.synchronize()
-    print('%s G%d B%d %dx%d Cin%d Cout%d k%d s%d: %.3f ms per call' % (k, G, B, H, W, Cin, Cout, K, stride, e0.elapsed_time(e1) / iters))
+    print('mode %s %s G%d B%d %dx%d Cin%d Cout%d k%d s%d: %.3f ms per call' % (os.environ.get('COUNCIL_TC_MODE', 'default'), k, G, B, H, W, Cin, Cout, K, stride, e0.elapsed_time(e1) / iters))
