@@ -185,7 +185,26 @@ struct TcParams {
 __device__ __forceinline__ void epilogue_store_coalesced(const float (&v)[32], float4* patch, int lane, long out_off, float* __restrict__ y,
                                                          const float* __restrict__ addend, const float* __restrict__ mask_src, int act,
                                                          float slope) {
-    const int wsw = (lane >> 1) & 3;
+    const int wsw = (lane >> 1) & 3, c4 = lane & 3;
+    long offs[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) offs[i] = __shfl_sync(0xffffffffu, out_off, i * 8 + (lane >> 2));
+    // every residual / mask load of the block is issued before the shared-memory round trip (one exposed latency, not eight)
+    float4 av[2][4], mv[2][4];
+    if (addend) {
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                av[half][i] = offs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(addend + offs[i] + half * 16 + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (mask_src) {
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                mv[half][i] = offs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(mask_src + offs[i] + half * 16 + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         __syncwarp();
@@ -195,17 +214,15 @@ __device__ __forceinline__ void epilogue_store_coalesced(const float (&v)[32], f
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int r = i * 8 + (lane >> 2), c4 = lane & 3;
+            const int r = i * 8 + (lane >> 2);
             float4 o = patch[r * 4 + (c4 ^ ((r >> 1) & 3))];
-            const long off = __shfl_sync(0xffffffffu, out_off, r);
-            if (off < 0) continue;
-            const long e = off + half * 16 + c4 * 4;
+            if (offs[i] < 0) continue;
             if (addend) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(addend + e));
+                const float4 a = av[half][i];
                 o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
             }
             if (mask_src) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(mask_src + e));
+                const float4 a = mv[half][i];
                 o.x *= a.x > 0.f ? 1.f : slope; o.y *= a.y > 0.f ? 1.f : slope;
                 o.z *= a.z > 0.f ? 1.f : slope; o.w *= a.w > 0.f ? 1.f : slope;
             } else if (act == CG_ACT_RELU) {
@@ -214,7 +231,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const float (&v)[32], f
                 o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
                 o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
             }
-            *reinterpret_cast<float4*>(y + e) = o;
+            *reinterpret_cast<float4*>(y + offs[i] + half * 16 + c4 * 4) = o;
         }
     }
 }
@@ -887,7 +904,9 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     while (cps > 1 && (cps > kiters || cps * chunk_bytes > 64 * 1024)) cps >>= 1;
     p.cps = cps;
     int stage_bytes = cps * chunk_bytes;
-    p.coalesce = g_epi_coalesce && p.bn >= 32 && p.act != CG_ACT_TANH ? 1 : 0;
+    // narrow tiles (<= 64 output channels) are the store-heavy ones; on the wide compute-bound tiles the patch traffic competes with the
+    // MMA operand reads for shared-memory bandwidth and measured 1-3 % slower (visit I): those keep the accumulator-layout stores
+    p.coalesce = g_epi_coalesce && p.bn >= 32 && (p.bn <= 64 || g_epi_coalesce == 2) && p.act != CG_ACT_TANH ? 1 : 0;
     const int stat_bytes = (p.stats ? 4 * 32 * 36 * 4 : 0) + (p.coalesce ? 4 * 2048 : 0);
     // narrow tiles are bound by the single MMA-issuing thread's per-stage latency: two co-resident CTAs per SM interleave their MMAs
     const bool two = g_fwd_2cta && p.bn <= 64 && !p.stats && 2 * stage_bytes <= 100 * 1024;
