@@ -7,6 +7,7 @@ namespace cg {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 thread_local int g_tc_mode = 7;
+thread_local int g_pdl = 1;  // programmatic dependent launch between this library's kernels (mode bit 22 clears it)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -54,6 +55,8 @@ static size_t patch_w_bytes(const cg_conv_geom& g) {
 
 __global__ void im2col_small_kernel(const float* __restrict__ x, float* __restrict__ P, long total4, int H, int W, int Cin, int Ho, int Wo,
                                     int KH, int KW, int stride, int pad, int K2, int K2p) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 slot of P
     if (i >= total4) return;
     int slots = K2p >> 2;
@@ -75,6 +78,8 @@ __global__ void im2col_small_kernel(const float* __restrict__ x, float* __restri
 }
 // rows of K2 floats <-> rows of K2p floats (zero padded); dir 0: pad (w -> wp), 1: unpad (dwp -> dw)
 __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long rows, int K2, int K2p, int dir) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (dir == 0) {
         if (i >= rows * K2p) return;
@@ -92,7 +97,7 @@ static int run_im2col(const cg_conv_geom& g, const float* x, float* P, cudaStrea
     cg_conv_geom p = patch_geom(g);
     long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
     long total4 = nimg * g.Ho * g.Wo * (p.Cin / 4);
-    im2col_small_kernel<<<cdiv(total4, 256), 256, 0, st>>>(x, P, total4, g.H, g.W, g.Cin, g.Ho, g.Wo, g.KH, g.KW, g.stride, g.pad,
+    launch_k(im2col_small_kernel, cdiv(total4, 256), 256, 0, st, x, P, total4, g.H, g.W, g.Cin, g.Ho, g.Wo, g.KH, g.KW, g.stride, g.pad,
                                                           g.KH * g.KW * g.Cin, p.Cin);
     return check_launch("im2col_small");
 }
@@ -133,6 +138,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
     g_fwd_2cta = ((mode >> 17) & 1) ? 0 : 1;    // bit 17: one forward / dgrad CTA per SM for tiles <= 64 wide (default: two co-resident)
     g_img_path = ((mode >> 19) & 1) ? 0 : 1;    // bit 19: image-side layers on the older paths (TMA im2col forward, explicit patch matrix weight gradient)
     g_epi_coalesce = ((mode >> 20) & 1) ? 0 : (((mode >> 21) & 1) ? 2 : 1);  // bit 20: accumulator-layout epilogue stores everywhere; bit 21: the coalescing patch on the wide tiles too
+    g_pdl = ((mode >> 22) & 1) ? 0 : 1;  // bit 22: plain stream-serialised launches
     g_pair_cap = (mode >> 8) & 0xff;  // bits 8..15: cap on the number of CTA pairs launched (0 = as many as are co-resident)
     return prev;
 }
@@ -201,7 +207,7 @@ extern "C" int cg_conv_fwd(const cg_conv_geom* g, const float* x, const float* w
         float* wp = (float*)((uint8_t*)ws + patch_bytes(*g));
         if (int rc = run_im2col(*g, x, P, st)) return rc;
         long rows = (long)g->G * g->Cout;
-        pad_rows_kernel<<<cdiv(rows * p.Cin, 256), 256, 0, st>>>(w, wp, rows, g->KH * g->KW * g->Cin, p.Cin, 0);
+        launch_k(pad_rows_kernel, cdiv(rows * p.Cin, 256), 256, 0, st, w, wp, rows, g->KH * g->KW * g->Cin, p.Cin, 0);
         if (int rc = check_launch("pad_rows")) return rc;
         return tc_conv_fwd(p, P, wp, bias, y, act, slope, nullptr, 0, st);
     }
@@ -248,7 +254,7 @@ extern "C" int cg_conv_wgrad(const cg_conv_geom* g, const float* x, const float*
         if (int rc = tc_conv_wgrad(p, P, dy, dwp, inner, inner_bytes, st)) return rc;
         long rows = (long)g->G * g->Cout;
         int K2 = g->KH * g->KW * g->Cin;
-        pad_rows_kernel<<<cdiv(rows * K2, 256), 256, 0, st>>>(dwp, dw, rows, K2, p.Cin, 1);
+        launch_k(pad_rows_kernel, cdiv(rows * K2, 256), 256, 0, st, dwp, dw, rows, K2, p.Cin, 1);
         if (int rc = check_launch("unpad_rows")) return rc;
         if (db) return colsum(dy, db, g->G, dp.Mpix, g->Cout, inner, inner_bytes, st);
         return CG_OK;

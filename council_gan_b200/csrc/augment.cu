@@ -15,6 +15,8 @@ namespace cg {
 // per-image L sums (exact integers: order-independent atomics) for the images whose current op is the contrast adjustment
 __global__ void __launch_bounds__(256) aug_lsum_kernel(const uint8_t* __restrict__ imgs, const int32_t* __restrict__ desc,
                                                        const int32_t* __restrict__ opcode, unsigned long long* __restrict__ lsum) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     if (opcode[b] != CG_AUG_CONTRAST) return;
     const int npix = desc[b * 4 + 1] * desc[b * 4 + 2];
@@ -29,6 +31,8 @@ __global__ void __launch_bounds__(256) aug_lsum_kernel(const uint8_t* __restrict
 __global__ void __launch_bounds__(256) aug_color_kernel(uint8_t* __restrict__ imgs, const int32_t* __restrict__ desc,
                                                         const int32_t* __restrict__ opcode, const float* __restrict__ param,
                                                         const unsigned long long* __restrict__ lsum) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int op = opcode[b];
     if (op == CG_AUG_NONE) return;
@@ -49,6 +53,8 @@ __global__ void __launch_bounds__(256) aug_resize_h_kernel(const uint8_t* __rest
                                                            const int32_t* __restrict__ flip, uint8_t* __restrict__ tmp,
                                                            const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
                                                            int H, int W, int ow) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y;
     const int total = H * ow;
     const uint8_t* src = imgs + src_off[n];
@@ -65,6 +71,8 @@ __global__ void __launch_bounds__(256) aug_resize_v_crop_kernel(const uint8_t* _
                                                                 const int32_t* __restrict__ crop, float* __restrict__ out_nhwc,
                                                                 float* __restrict__ out_nchw, const int32_t* __restrict__ bounds,
                                                                 const int32_t* __restrict__ kk, int ksize, int H, int ow, int ch, int cw) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y;
     const int total = ch * cw;
     const uint8_t* src = tmp + (long)n * H * ow * 3;
@@ -98,10 +106,10 @@ extern "C" int cg_aug_color(uint8_t* imgs, const int32_t* desc, const int32_t* o
             set_error("aug_color: %s", cudaGetErrorString(e));
             return CG_ERR_CUDA;
         }
-        aug_lsum_kernel<<<dim3(blocks, B), 256, 0, st>>>(imgs, desc, opcode, lsum);
+        launch_k(aug_lsum_kernel, dim3(blocks, B), 256, 0, st, imgs, desc, opcode, lsum);
         if (int rc = check_launch("aug_lsum")) return rc;
     }
-    aug_color_kernel<<<dim3(blocks, B), 256, 0, st>>>(imgs, desc, opcode, param, lsum);
+    launch_k(aug_color_kernel, dim3(blocks, B), 256, 0, st, imgs, desc, opcode, param, lsum);
     return check_launch("aug_color");
 }
 
@@ -113,10 +121,10 @@ extern "C" int cg_aug_resize_crop(const uint8_t* imgs, const int32_t* src_off, c
     cudaStream_t st = (cudaStream_t)stream;
     int b1 = cdiv((long)H * ow, 256);
     if (b1 > 256) b1 = 256;
-    aug_resize_h_kernel<<<dim3(b1, n), 256, 0, st>>>(imgs, src_off, flip, tmp, bounds_h, kk_h, ksize_h, H, W, ow);
+    launch_k(aug_resize_h_kernel, dim3(b1, n), 256, 0, st, imgs, src_off, flip, tmp, bounds_h, kk_h, ksize_h, H, W, ow);
     if (int rc = check_launch("aug_resize_h")) return rc;
     int b2 = cdiv((long)ch * cw, 256);
     if (b2 > 256) b2 = 256;
-    aug_resize_v_crop_kernel<<<dim3(b2, n), 256, 0, st>>>(tmp, slot, crop, out_nhwc, out_nchw, bounds_v, kk_v, ksize_v, H, ow, ch, cw);
+    launch_k(aug_resize_v_crop_kernel, dim3(b2, n), 256, 0, st, tmp, slot, crop, out_nhwc, out_nchw, bounds_v, kk_v, ksize_v, H, ow, ch, cw);
     return check_launch("aug_resize_v_crop");
 }

@@ -55,6 +55,32 @@ inline int check_launch(const char* what) {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------------------
+// A training step is ~670 short-to-medium kernels in one stream.  Every kernel of this library (a) lets its successor start launching
+// at once (griddepcontrol.launch_dependents as its first instruction: CTAs of the next kernel are scheduled as SM resources free up and run
+// their on-chip prologue -- barrier init, TMEM allocation, tensor-map prefetch) and (b) executes griddepcontrol.wait before it touches
+// global memory: that blocks until the WHOLE preceding grid has completed and its writes are visible, so the data dependences are
+// exactly those of plain stream order (every kernel waits, so completion is transitive along the stream).  Kernels of other libraries
+// (NCCL, memsets, copies) are launched without the attribute and keep full stream serialisation on both sides.
+extern thread_local int g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through check_launch()'s cudaGetLastError
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == CG_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == CG_ACT_LRELU) return v > 0.f ? v : v * slope;

@@ -42,6 +42,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // =====================================================================================================================
 template <int L, int KW>
 __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const __grid_constant__ ImgP p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1k(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,6 +229,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_fwd_kernel(const __gr
 // stage = [4 M groups of 32 k-rows][kp pixels x 128 B] (patches, built here) + [2 N groups of 32 couts][kp x 128 B] (dy, TMA)
 template <int L, int KW, int KP>
 __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_wgrad_kernel(const __grid_constant__ ImgP p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1k(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -375,6 +379,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) img_conv_wgrad_kernel(const __
 // dw[g][co][k] = sum_split part[split][g][k][co];  db[g][co] = sum_split part[split][g][K][co]   (fixed order: deterministic)
 __global__ void img_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int G, int K,
                                         int splits) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over G * (K+1) * 64
     const int total = G * (K + 1) * 64;
     if (i >= total) return;
@@ -438,7 +444,7 @@ int img_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const fl
             return CG_ERR_CUDA;
         }
     }
-    kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
+    launch_k(kern, p.G * p.cpg, IMG_THREADS, smem, st, p);
     return check_launch("img_conv_fwd");
 }
 
@@ -476,10 +482,10 @@ int img_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float
             return CG_ERR_CUDA;
         }
     }
-    kern<<<p.G * p.cpg, IMG_THREADS, smem, st>>>(p);
+    launch_k(kern, p.G * p.cpg, IMG_THREADS, smem, st, p);
     if (int rc = check_launch("img_conv_wgrad")) return rc;
     const int total = g.G * (p.K + 1) * 64;
-    img_wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.part, dw, db, g.G, p.K, p.cpg);
+    launch_k(img_wgrad_reduce_kernel, cdiv(total, 256), 256, 0, st, p.part, dw, db, g.G, p.K, p.cpg);
     return check_launch("img_wgrad_reduce");
 }
 

@@ -44,6 +44,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // forward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) conv_fwd_simt_kernel(ConvKP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[BK][BM + SPAD];
     __shared__ __align__(16) float Bs[BK][BN + SPAD];
     const int tid = threadIdx.x;
@@ -156,7 +158,7 @@ int simt_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const f
     ConvKP p = make_kp(g);
     p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act; p.slope = slope;
     dim3 grid(cdiv(p.Mpix, BM), cdiv(p.Cout, BN), p.G);
-    conv_fwd_simt_kernel<<<grid, NT, 0, st>>>(p);
+    launch_k(conv_fwd_simt_kernel, grid, NT, 0, st, p);
     return check_launch("conv_fwd_simt");
 }
 
@@ -164,6 +166,8 @@ int simt_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const f
 // data gradient (w.r.t. the tensor the convolution sees: [G][B][Hin][Win][Cin])
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) conv_dgrad_simt_kernel(ConvKP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[BK][BM + SPAD];
     __shared__ __align__(16) float Bs[BK][BN + SPAD];
     const int tid = threadIdx.x;
@@ -310,7 +314,7 @@ int simt_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, floa
     int s = g.stride;
     long Mc = (long)g.B * cdiv(p.Hin, s) * cdiv(p.Win, s);
     dim3 grid(cdiv(Mc, BM), cdiv(p.Cin, BN), p.G * s * s);
-    conv_dgrad_simt_kernel<<<grid, NT, 0, st>>>(p);
+    launch_k(conv_dgrad_simt_kernel, grid, NT, 0, st, p);
     return check_launch("conv_dgrad_simt");
 }
 
@@ -318,6 +322,8 @@ int simt_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, floa
 // weight gradient (split-K over pixels, deterministic two-phase reduction)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(ConvKP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[BK][BM + SPAD];  // [pixel][co]
     __shared__ __align__(16) float Bs[BK][BN + SPAD];  // [pixel][n]
     const int tid = threadIdx.x;
@@ -420,6 +426,8 @@ __global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(ConvKP p) {
 }
 
 __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, long n4, int splits) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -462,12 +470,12 @@ int simt_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, floa
     float* out = p.splits == 1 ? dw : reinterpret_cast<float*>(ws);
     p.x = x; p.y = const_cast<float*>(dy); p.w = out;
     dim3 grid(cdiv(p.Ktot, BN), cdiv(p.Cout, BM), p.G * p.splits);
-    conv_wgrad_simt_kernel<<<grid, NT, 0, st>>>(p);
+    launch_k(conv_wgrad_simt_kernel, grid, NT, 0, st, p);
     int rc = check_launch("conv_wgrad_simt");
     if (rc) return rc;
     if (p.splits > 1) {
         long n4 = (long)p.G * p.Cout * p.Ktot / 4;
-        reduce_splits_kernel<<<cdiv(n4, 256), 256, 0, st>>>(out, dw, n4, p.splits);
+        launch_k(reduce_splits_kernel, cdiv(n4, 256), 256, 0, st, out, dw, n4, p.splits);
         rc = check_launch("reduce_splits");
     }
     return rc;
@@ -484,6 +492,8 @@ static inline int cs_rows(long rows) {
 }
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
                                                              long rows, int C, int nchunks, int CS_ROWS) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[256];
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int cpp = C < 256 ? C : 256;
@@ -508,6 +518,8 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int GC, int nchunks) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= GC) return;
     float s = 0.f;
@@ -517,6 +529,8 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 // float4-vectorised variant for C % 4 == 0, C/4 dividing 256: lanes = C/4 threads across channels, 256/lanes row lanes
 __global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __restrict__ dy, float* __restrict__ part, long rows, int C,
                                                                 int CS_ROWS) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sm[256];
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int lanes = C >> 2, rowl = 256 / lanes;
@@ -555,12 +569,12 @@ int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t
     const int csr = cs_rows(rows);
     int nchunks = cdiv(rows, csr);
     if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
-        colsum_partial_v4_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, csr);
+        launch_k(colsum_partial_v4_kernel, dim3(nchunks, G), 256, 0, st, dy, (float*)ws, rows, C, csr);
     else
-        colsum_partial_kernel<<<dim3(nchunks, G), 256, 0, st>>>(dy, (float*)ws, rows, C, nchunks, csr);
+        launch_k(colsum_partial_kernel, dim3(nchunks, G), 256, 0, st, dy, (float*)ws, rows, C, nchunks, csr);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
-    colsum_final_kernel<<<cdiv((long)G * C, 256), 256, 0, st>>>((const float*)ws, db, G * C, nchunks);
+    launch_k(colsum_final_kernel, cdiv((long)G * C, 256), 256, 0, st, (const float*)ws, db, G * C, nchunks);
     return check_launch("colsum_final");
 }
 
@@ -570,6 +584,8 @@ int colsum(const float* dy, float* db, int G, long rows, int C, void* ws, size_t
 // ------------------------------------------------------------------------------------------------
 __global__ void pool2x2_sum_kernel(const float* __restrict__ d_up, float* __restrict__ dx, const float* __restrict__ addend,
                                    const float* __restrict__ mask_src, float slope, long total4, int H, int W, int C4) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     int c = (int)(i % C4);
@@ -598,7 +614,7 @@ __global__ void pool2x2_sum_kernel(const float* __restrict__ d_up, float* __rest
 int pool2x2_sum(const float* d_up, float* dx, const float* addend, const float* mask_src, float mask_slope,
                 long N, int H, int W, int C, cudaStream_t st) {
     long total4 = N * H * W * (C / 4);
-    pool2x2_sum_kernel<<<cdiv(total4, 256), 256, 0, st>>>(d_up, dx, addend, mask_src, mask_slope, total4, H, W, C / 4);
+    launch_k(pool2x2_sum_kernel, cdiv(total4, 256), 256, 0, st, d_up, dx, addend, mask_src, mask_slope, total4, H, W, C / 4);
     return check_launch("pool2x2_sum");
 }
 

@@ -18,6 +18,8 @@ __device__ __forceinline__ float4 s_ld4(const float* p) { return __ldg(reinterpr
 // ---- Cout == 1 head: forward ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ y, long npix, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.y;
     const long px = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (px >= npix) return;
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(256) head1_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) head1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                                                           const float* __restrict__ addend, const float* __restrict__ mask_src, float slope,
                                                           long npix, int C4) {
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.y;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over npix * C4
     if (i >= npix * C4) return;
@@ -63,6 +67,8 @@ constexpr int H1_ROWS = 256;  // pixels per block
 // part[chunk][g][C + 4]: columns 0..C-1 = sum dy*x, column C = sum dy
 __global__ void __launch_bounds__(256) head1_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
                                                                   long npix, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sm[256];
     __shared__ float sdy[8];
     const int g = blockIdx.y, chunk = blockIdx.x;
@@ -99,6 +105,8 @@ __global__ void __launch_bounds__(256) head1_wgrad_partial_kernel(const float* _
     }
 }
 __global__ void head1_wgrad_final_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int G, int C, int nchunks) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over G * (C + 1)
     if (i >= G * (C + 1)) return;
     const int g = i / (C + 1), c = i - g * (C + 1);
@@ -114,6 +122,8 @@ constexpr int LD_MAXB = 16;
 // part[slice][g][b][Cin]
 __global__ void __launch_bounds__(256) lin_dgrad_partial_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ part,
                                                                 int B, int Cin, int Cout) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sdy[LD_MAXB][LD_SLICE];
     const int g = blockIdx.y, slice = blockIdx.x;
     const int co0 = slice * LD_SLICE, n = min(LD_SLICE, Cout - co0);
@@ -140,6 +150,8 @@ __global__ void __launch_bounds__(256) lin_dgrad_partial_kernel(const float* __r
 }
 __global__ void lin_dgrad_final_kernel(const float* __restrict__ part, float* __restrict__ dx, const float* __restrict__ addend,
                                        const float* __restrict__ mask_src, float slope, long total, int nslices) {
+    pdl_trigger();
+    pdl_wait();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over G * B * Cin
     if (i >= total) return;
     float s = 0.f;
@@ -170,7 +182,7 @@ size_t small_ws(const cg_conv_geom& g, int which) {
 
 int small_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
     const long npix = (long)g.B * g.H * g.W;
-    head1_fwd_kernel<<<dim3(cdiv(npix, 8), g.G), 256, 0, st>>>(x, w, bias, y, npix, g.Cin);
+    launch_k(head1_fwd_kernel, dim3(cdiv(npix, 8), g.G), 256, 0, st, x, w, bias, y, npix, g.Cin);
     return check_launch("head1_fwd");
 }
 
@@ -179,7 +191,7 @@ int small_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, flo
     if (is_head1(g)) {
         const long npix = (long)g.B * g.H * g.W;
         const int C4 = g.Cin / 4;
-        head1_dgrad_kernel<<<dim3(cdiv(npix * C4, 256), g.G), 256, 0, st>>>(dy, w, dx, addend, mask_src, slope, npix, C4);
+        launch_k(head1_dgrad_kernel, dim3(cdiv(npix * C4, 256), g.G), 256, 0, st, dy, w, dx, addend, mask_src, slope, npix, C4);
         return check_launch("head1_dgrad");
     }
     size_t need = small_ws(g, 1);
@@ -188,10 +200,10 @@ int small_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, flo
         return CG_ERR_WORKSPACE;
     }
     const int nsl = cdiv(g.Cout, LD_SLICE);
-    lin_dgrad_partial_kernel<<<dim3(nsl, g.G), 256, 0, st>>>(dy, w, (float*)ws, g.B, g.Cin, g.Cout);
+    launch_k(lin_dgrad_partial_kernel, dim3(nsl, g.G), 256, 0, st, dy, w, (float*)ws, g.B, g.Cin, g.Cout);
     if (int rc = check_launch("lin_dgrad_partial")) return rc;
     const long total = (long)g.G * g.B * g.Cin;
-    lin_dgrad_final_kernel<<<cdiv(total, 256), 256, 0, st>>>((const float*)ws, dx, addend, mask_src, slope, total, nsl);
+    launch_k(lin_dgrad_final_kernel, cdiv(total, 256), 256, 0, st, (const float*)ws, dx, addend, mask_src, slope, total, nsl);
     return check_launch("lin_dgrad_final");
 }
 
@@ -203,9 +215,9 @@ int small_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, flo
     }
     const long npix = (long)g.B * g.H * g.W;
     const int nchunks = cdiv(npix, H1_ROWS);
-    head1_wgrad_partial_kernel<<<dim3(nchunks, g.G), 256, 0, st>>>(x, dy, (float*)ws, npix, g.Cin);
+    launch_k(head1_wgrad_partial_kernel, dim3(nchunks, g.G), 256, 0, st, x, dy, (float*)ws, npix, g.Cin);
     if (int rc = check_launch("head1_wgrad_partial")) return rc;
-    head1_wgrad_final_kernel<<<cdiv(g.G * (g.Cin + 1), 256), 256, 0, st>>>((const float*)ws, dw, db, g.G, g.Cin, nchunks);
+    launch_k(head1_wgrad_final_kernel, cdiv(g.G * (g.Cin + 1), 256), 256, 0, st, (const float*)ws, dw, db, g.G, g.Cin, nchunks);
     return check_launch("head1_wgrad_final");
 }
 

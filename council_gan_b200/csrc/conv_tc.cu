@@ -238,6 +238,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const float (&v)[32], f
 
 template <int BK>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // on-chip prologue done (barriers, TMEM): from here on the kernel reads what its predecessors in the stream wrote
 
     if (warp == TC_PRODUCER_WARP) {
         // ===================== TMA producer =====================
@@ -568,6 +570,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on `
 constexpr int TC2_MAX_STAGES = 12;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -617,6 +620,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // on-chip prologue done (barriers, TMEM): from here on the kernel reads what its predecessors in the stream wrote
 
     if (warp == TC_PRODUCER_WARP) {
         if (lane == 0) {
@@ -970,13 +974,13 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
         if (int rc = encode_weights_map(&p.bmap, p.w_base, p.w_rows, p.w_ktot, p.bn / 2, 32)) return rc;  // each CTA stages half of the rows
         long ptiles = (long)p.G * p.ncls * (p.Cout / p.bn) * cdiv((long)p.B * p.P * p.Q, 2 * TC_BM);
         int nclusters = (int)(ptiles < pairs ? ptiles : pairs);
-        conv_tc2_kernel<<<2 * nclusters, TC_THREADS, smem2, st>>>(p);
+        launch_k(conv_tc2_kernel, 2 * nclusters, TC_THREADS, smem2, st, p);
         return check_launch("conv_tc2_kernel");
     }
     const long slots = (long)sm_count_now() * (two ? 2 : 1);
     int grid = (int)(tiles < slots ? tiles : slots);
-    if (p.bk == 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(p);
-    else conv_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(p);
+    if (p.bk == 32) launch_k(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, p);
+    else launch_k(conv_tc_kernel<8>, grid, TC_THREADS, smem, st, p);
     return check_launch("conv_tc_kernel");
 }
 
@@ -985,6 +989,8 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
 // collapse onto those 2 source rows: a=0 -> {w0, w1+w2}, a=1 -> {w0+w1, w2} (same along columns).  2.25x fewer
 // FLOPs than convolving the materialised upsampled tensor, and the upsampled tensor never exists.
 __global__ void ups_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wc, long total, int Cout, int Cin) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // wc[g][cls][co][r][s][ci]
     if (i >= total) return;
     int ci = (int)(i % Cin);
@@ -1038,7 +1044,7 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
         }
         float* wc = (float*)ws;
         long total = (long)g.G * 4 * g.Cout * 4 * g.Cin;
-        ups_weight_transform_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, wc, total, g.Cout, g.Cin);
+        launch_k(ups_weight_transform_kernel, cdiv(total, 256), 256, 0, st, w, wc, total, g.Cout, g.Cin);
         if (int rc = check_launch("ups_weight_transform")) return rc;
         if (int rc = encode_weights_map_p(p, wc, (long)g.G * 4 * g.Cout, 4L * g.Cin)) return rc;
         for (int c = 0; c < 4; c++) {
@@ -1083,6 +1089,8 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
 // transposed copy); grid = (co tiles x ci tiles, KH*KW, G)
 __global__ void __launch_bounds__(256) dgrad_weight_transform_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin,
                                                                      int CinP, int KH, int KW, int s) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int TH = KH / s, TW = KW / s;
     const int cit = (CinP + 31) / 32;
@@ -1144,7 +1152,7 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
     float* d_seen = g.ups ? (float*)((uint8_t*)ws + wt_bytes) : dx;
     long total = (long)g.G * g.Cout * g.KH * g.KW * CinP;
     (void)total;
-    dgrad_weight_transform_kernel<<<dim3(cdiv(g.Cout, 32) * cdiv(CinP, 32), g.KH * g.KW, g.G), dim3(32, 8), 0, st>>>(w, wt, g.Cout, g.Cin, CinP,
+    launch_k(dgrad_weight_transform_kernel, dim3(cdiv(g.Cout, 32) * cdiv(CinP, 32), g.KH * g.KW, g.G), dim3(32, 8), 0, st, w, wt, g.Cout, g.Cin, CinP,
                                                                                                                   g.KH, g.KW, s);
     if (int rc = check_launch("dgrad_weight_transform")) return rc;
 
@@ -1215,6 +1223,7 @@ struct WgParams {
 // between 4-row K groups (512 B); one K=8 MMA consumes two K groups.
 
 __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1260,6 +1269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // on-chip prologue done (barriers, TMEM): from here on the kernel reads what its predecessors in the stream wrote
 
     // unit -> (g, cot, split, cit, tap group), tap group fastest so CTAs running together share the dy tile in L2
     auto decode = [&](int u, int& g, int& cot, int& sp, int& cit, int& tg) {
@@ -1393,6 +1403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const __grid_co
 // channels and HALF of the x columns of every tap (N/2), so a 64-pixel stage is 64 KB instead of 96 KB (3 stages deep
 // instead of 2, 8 TMA boxes instead of 12) and the x tile crosses L2 -> shared memory once per 256 output channels.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad_tc2_kernel(const __grid_constant__ WgParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1440,6 +1451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // on-chip prologue done (barriers, TMEM): from here on the kernel reads what its predecessors in the stream wrote
 
     auto decode = [&](int u, int& g, int& cot, int& sp, int& cit, int& tg) {
         tg = u % TG; u /= TG;
@@ -1572,6 +1584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) wgrad
 // operand (N = Cout).  D[(tap, ci)][co] is written back transposed: for a fixed co the 32 lanes of a warp hold 32
 // consecutive ci = one 128-byte store.  Up to Tm row tiles share the dy stage.
 __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_xm_kernel(const __grid_constant__ WgParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1618,6 +1631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_xm_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // on-chip prologue done (barriers, TMEM): from here on the kernel reads what its predecessors in the stream wrote
 
     // unit -> (g, split, row-tile group), row-tile group fastest so CTAs running together share the dy tile in L2
     auto decode = [&](int u, int& g, int& sp, int& mg) {
@@ -1747,6 +1761,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_xm_kernel(const __grid_co
 }
 
 __global__ void reduce_splits_tc_kernel(const float* __restrict__ part, float* __restrict__ out, long n4, int splits) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1945,11 +1961,11 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         const int slots = sm_count_now() * (two ? 2 : 1);
         int grid = (int)(units < slots ? units : slots);
         if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_xm: units=%ld splits=%d chunk=%ld stages=%d Tm=%d kp=%d\n", units, p.splits, p.chunk, stages, p.Tm, p.kp);
-        wgrad_xm_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+        launch_k(wgrad_xm_kernel, grid, TC_THREADS, smem, st, p);
         if (int rc = check_launch("wgrad_xm_kernel")) return rc;
         if (p.splits > 1) {
             long n4 = (long)g.G * g.Cout * g.KH * g.KW * g.Cin / 4;
-            reduce_splits_tc_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float*)ws, dw, n4, p.splits);
+            launch_k(reduce_splits_tc_kernel, cdiv(n4, 256), 256, 0, st, (const float*)ws, dw, n4, p.splits);
             return check_launch("reduce_splits_tc");
         }
         return CG_OK;
@@ -1972,11 +1988,11 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
         int pairs = sm_count_now() / 2;
         int nclusters = (int)(units < pairs ? units : pairs);
         if (getenv("COUNCIL_DEBUG")) fprintf(stderr, "wgrad_tc2: units=%ld splits=%d chunk=%ld stages=%d T=%d bn=%d kp=%d\n", units, p.splits, p.chunk, stages, p.T, p.bn, p.kp);
-        wgrad_tc2_kernel<<<2 * nclusters, TC_THREADS, smem, st>>>(p);
+        launch_k(wgrad_tc2_kernel, 2 * nclusters, TC_THREADS, smem, st, p);
         if (int rc = check_launch("wgrad_tc2_kernel")) return rc;
         if (p.splits > 1) {
             long n4 = (long)g.G * g.Cout * g.KH * g.KW * g.Cin / 4;
-            reduce_splits_tc_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float*)ws, dw, n4, p.splits);
+            launch_k(reduce_splits_tc_kernel, cdiv(n4, 256), 256, 0, st, (const float*)ws, dw, n4, p.splits);
             return check_launch("reduce_splits_tc");
         }
         return CG_OK;
@@ -2000,11 +2016,11 @@ int tc_conv_wgrad(const cg_conv_geom& g, const float* x, const float* dy, float*
     long units = (long)g.G * ((g.Cout + 127) / 128) * p.splits * (g.Cin / p.bn) * ((g.KH * g.KW + p.T - 1) / p.T);
     const int slots = sm_count_now() * (two ? 2 : 1);
     int grid = (int)(units < slots ? units : slots);
-    wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+    launch_k(wgrad_tc_kernel, grid, TC_THREADS, smem, st, p);
     if (int rc = check_launch("wgrad_tc_kernel")) return rc;
     if (p.splits > 1) {
         long n4 = (long)g.G * g.Cout * g.KH * g.KW * g.Cin / 4;
-        reduce_splits_tc_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float*)ws, dw, n4, p.splits);
+        launch_k(reduce_splits_tc_kernel, cdiv(n4, 256), 256, 0, st, (const float*)ws, dw, n4, p.splits);
         return check_launch("reduce_splits_tc");
     }
     return CG_OK;

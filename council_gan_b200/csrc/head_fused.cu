@@ -42,6 +42,8 @@ __device__ __forceinline__ void stage_weights(uint8_t* dst, const float* w, int 
 }
 
 __global__ void __launch_bounds__(HD_THREADS, 3) head_fused_kernel(const HeadP p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -231,6 +233,6 @@ extern "C" int cg_head_fused(const float* y, const float* mean, const float* rst
             return CG_ERR_CUDA;
         }
     }
-    head_fused_kernel<<<G * p.cpg, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    launch_k(head_fused_kernel, G * p.cpg, HD_THREADS, smem, (cudaStream_t)stream, p);
     return check_launch("head_fused");
 }

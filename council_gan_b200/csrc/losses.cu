@@ -58,6 +58,8 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned 
 __global__ void __launch_bounds__(256) lsgan_fused_kernel(const cg_lsgan_desc d, float* __restrict__ loss_total, int accumulate,
                                                           float* __restrict__ loss_plain, float* __restrict__ part,
                                                           unsigned int* __restrict__ counter) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[32];
     const int nseg = d.nseg, G = d.G;
     int b = blockIdx.x;
@@ -108,6 +110,8 @@ constexpr int GL_PIX = 2048;  // mask pixels per focus block
 // ws: float part_map[nmaps][G]; float part_focus[nchunks][G][4]; ticket counter.
 __global__ void __launch_bounds__(256) gen_loss_fwd_kernel(const cg_gen_loss_desc d, float* __restrict__ scal, float* __restrict__ part_map,
                                                            float* __restrict__ part_focus, unsigned int* __restrict__ counter, int nchunks) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[4 * 32];
     const int G = d.G, nmaps = d.n_adv + d.n_cl;
     const int b = blockIdx.x;
@@ -209,6 +213,8 @@ __global__ void __launch_bounds__(256) gen_loss_bwd_kernel(const cg_gen_loss_des
                                                            double* __restrict__ hist_gan, double* __restrict__ hist_council,
                                                            float* __restrict__ total, double* __restrict__ total64, int accumulate,
                                                            float* __restrict__ pub, float* __restrict__ d_mask, int map_blocks) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ GenCoef sc[CG_LOSS_MAX_G];
     const int G = d.G;
     const int R = hp.hist_size + 1;
@@ -346,7 +352,7 @@ extern "C" int cg_lsgan_fused(const cg_lsgan_desc* d, float* loss_total, int acc
     }
     for (int m = 0; m < d->nmaps; m++) CG_REQUIRE(d->out[m] && d->n_per_seg[m] > 0, "lsgan_fused: map %d is empty", m);
     int blocks = d->nmaps * d->G * d->nseg;
-    lsgan_fused_kernel<<<blocks, 256, 0, ST>>>(*d, loss_total, accumulate, loss_plain, ws_part(ws), ws_counter(ws));
+    launch_k(lsgan_fused_kernel, blocks, 256, 0, ST, *d, loss_total, accumulate, loss_plain, ws_part(ws), ws_counter(ws));
     return check_launch("lsgan_fused");
 }
 
@@ -378,7 +384,7 @@ extern "C" int cg_gen_loss_fwd(const cg_gen_loss_desc* d, float* scal, void* ws,
     }
     float* part_map = ws_part(ws);
     float* part_focus = part_map + (size_t)nmaps * d->G;
-    gen_loss_fwd_kernel<<<blocks, 256, 0, ST>>>(*d, scal, part_map, part_focus, ws_counter(ws), nchunks);
+    launch_k(gen_loss_fwd_kernel, blocks, 256, 0, ST, *d, scal, part_map, part_focus, ws_counter(ws), nchunks);
     return check_launch("gen_loss_fwd");
 }
 
@@ -396,7 +402,7 @@ extern "C" int cg_gen_loss_bwd(const cg_gen_loss_desc* d, const cg_gen_loss_hp* 
     if (px_blocks > 148 * 8) px_blocks = 148 * 8;  // grid-stride: each block pays the finalise prologue once
     int blocks = map_blocks + px_blocks;
     if (blocks == 0) blocks = 1;  // the finalise / publish step always runs
-    gen_loss_bwd_kernel<<<blocks, 256, 0, ST>>>(*d, *hp, scal, hist_gan, hist_council, total, ws_total64(ws), accumulate, pub, d_mask,
+    launch_k(gen_loss_bwd_kernel, blocks, 256, 0, ST, *d, *hp, scal, hist_gan, hist_council, total, ws_total64(ws), accumulate, pub, d_mask,
                                                 map_blocks);
     return check_launch("gen_loss_bwd");
 }

@@ -29,6 +29,8 @@ __device__ __forceinline__ float4 f4ld(const float* p) { return __ldg(reinterpre
 // part[chunk][gb][C][2] = (sum, sum of squares) of a pixel chunk
 __global__ void __launch_bounds__(256) in_stats_partial_kernel(const float* __restrict__ y, float* __restrict__ part,
                                                                int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sm[2][256];
     const int gb = blockIdx.y, chunk = blockIdx.x;
     LaneMap lm(C);
@@ -87,6 +89,8 @@ __device__ __forceinline__ bool final_sums(const float* __restrict__ part, long 
 __global__ void __launch_bounds__(FIN_ITEMS * FIN_SLICES) in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ mean,
                                                                                  float* __restrict__ rstd, long GBC, int nchunks, int HW,
                                                                                  float eps) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * FIN_ITEMS + threadIdx.x;
     double s, q;
     if (!final_sums(part, GBC, nchunks, i, s, q)) return;
@@ -117,6 +121,8 @@ __device__ __forceinline__ void affine_for(const NormP& p, int gb, int c, float4
 }
 
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormP p) {
+    pdl_trigger();
+    pdl_wait();
     const int gb = blockIdx.y;
     const int HW = p.H * p.W;
     LaneMap lm(p.C);
@@ -176,6 +182,8 @@ __device__ __forceinline__ float4 load_dz(const NormP& p, int gb, int r, int c) 
 
 // phase 1: part[chunk][gb][C][2] = (sum g1, sum g1*xhat), g1 = dz * act'(pre)
 __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(NormP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sm[2][256];
     const int gb = blockIdx.y;
     const int HW = p.H * p.W;
@@ -232,6 +240,8 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(NormP p) {
 __global__ void __launch_bounds__(FIN_ITEMS * FIN_SLICES) norm_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ sums,
                                                                                  float* __restrict__ d_adain, int GB, int C, int P, int off,
                                                                                  int nchunks) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * FIN_ITEMS + threadIdx.x;
     long GBC = (long)GB * C;
     double s, q;
@@ -246,6 +256,8 @@ __global__ void __launch_bounds__(FIN_ITEMS * FIN_SLICES) norm_bwd_final_kernel(
 }
 // phase 2: dy = gamma*rstd * (g1 - mean(g1) - xhat*mean(g1*xhat))
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormP p, const float* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int gb = blockIdx.y;
     const int HW = p.H * p.W;
     LaneMap lm(p.C);
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormP p, const floa
 }
 
 int in_stats_finalize(const float* part, float* mean, float* rstd, long GBC, int nchunks, int HW, float eps, cudaStream_t st) {
-    in_stats_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>(part, mean, rstd, GBC, nchunks, HW, eps);
+    launch_k(in_stats_final_kernel, cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st, part, mean, rstd, GBC, nchunks, HW, eps);
     return check_launch("in_stats_final");
 }
 
@@ -315,10 +327,10 @@ extern "C" int cg_in_stats(const float* y, float* mean, float* rstd, int G, int 
         return CG_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    in_stats_partial_kernel<<<dim3(nchunks, G * B), 256, 0, st>>>(y, (float*)ws, HW, C);
+    launch_k(in_stats_partial_kernel, dim3(nchunks, G * B), 256, 0, st, y, (float*)ws, HW, C);
     if (int rc = check_launch("in_stats_partial")) return rc;
     long GBC = (long)G * B * C;
-    in_stats_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>((const float*)ws, mean, rstd, GBC, nchunks, HW, eps);
+    launch_k(in_stats_final_kernel, cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st, (const float*)ws, mean, rstd, GBC, nchunks, HW, eps);
     return check_launch("in_stats_final");
 }
 
@@ -330,7 +342,7 @@ extern "C" int cg_norm_act_fwd(const float* y, const float* mean, const float* r
     NormP p{};
     p.y = y; p.mean = mean; p.rstd = rstd; p.adain = adain; p.res = res; p.z = z;
     p.P = P; p.off = off; p.B = B; p.H = H; p.W = W; p.C = C; p.act = act; p.ups = ups;
-    norm_act_fwd_kernel<<<dim3(cdiv((long)H * W, ST_ROWS), G * B), 256, 0, (cudaStream_t)stream>>>(p);
+    launch_k(norm_act_fwd_kernel, dim3(cdiv((long)H * W, ST_ROWS), G * B), 256, 0, (cudaStream_t)stream, p);
     return check_launch("norm_act_fwd");
 }
 
@@ -353,11 +365,11 @@ extern "C" int cg_norm_act_bwd(const float* dz, const float* y, const float* mea
     p.part = (float*)ws;
     float* sums = (float*)ws + (size_t)nchunks * GBC * 2;
     dim3 grid(nchunks, G * B);
-    norm_bwd_partial_kernel<<<grid, 256, 0, st>>>(p);
+    launch_k(norm_bwd_partial_kernel, grid, 256, 0, st, p);
     if (int rc = check_launch("norm_bwd_partial")) return rc;
-    norm_bwd_final_kernel<<<cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st>>>(p.part, sums, adain ? d_adain : nullptr, G * B, C, P, off,
+    launch_k(norm_bwd_final_kernel, cdiv(GBC, FIN_ITEMS), dim3(FIN_ITEMS, FIN_SLICES), 0, st, p.part, sums, adain ? d_adain : nullptr, G * B, C, P, off,
                                                                                        nchunks);
     if (int rc = check_launch("norm_bwd_final")) return rc;
-    norm_bwd_apply_kernel<<<grid, 256, 0, st>>>(p, sums);
+    launch_k(norm_bwd_apply_kernel, grid, 256, 0, st, p, sums);
     return check_launch("norm_bwd_apply");
 }

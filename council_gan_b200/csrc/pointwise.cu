@@ -34,6 +34,8 @@ __device__ __forceinline__ void block_reduce(float (&v)[N], float* smem /* >= N*
 // mask_k = (tanh(10*h[9+k])+1)/2;  im <- (1-mask_k)*im + mask_k*o_k, k = 0..2, starting from x_in
 __global__ void mask_head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ x_in, float* __restrict__ x_fake,
                                      float* __restrict__ mask, long total, long per_group) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float* hp = h + i * 12;
@@ -53,6 +55,8 @@ __global__ void mask_head_fwd_kernel(const float* __restrict__ h, const float* _
 __global__ void mask_head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ x_in,
                                      const float* __restrict__ d_xfake, const float* __restrict__ d_mask,
                                      float* __restrict__ dh_pre, long total, long per_group) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float* hp = h + i * 12;
@@ -101,6 +105,8 @@ __global__ void mask_head_bwd_kernel(const float* __restrict__ h, const float* _
 
 // ---- AvgPool2d(3, stride 2, pad 1, count_include_pad=False): networks.py:32,129 ------------------
 __global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int H, int W, int C4) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int Ho = H / 2, Wo = W / 2;
@@ -138,6 +144,8 @@ __device__ __forceinline__ int pool_cnt(int o, int L) {  // valid taps of output
 // one thread per input pixel; gathers from the <=2x2 output windows that cover it
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long total, int H, int W, int Cy,
                                    int Cx, int nch, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int Ho = H / 2, Wo = W / 2;
@@ -162,6 +170,8 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restri
 }
 
 __global__ void acc_slice_kernel(float* __restrict__ dst, const float* __restrict__ src, long npix, int Cd, int Cs, int nch) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     for (int c = 0; c < nch; c++) dst[i * Cd + c] += __ldg(src + i * Cs + c);
@@ -170,6 +180,8 @@ __global__ void acc_slice_kernel(float* __restrict__ dst, const float* __restric
 __global__ void gather_images_kernel(const float* __restrict__ pool0, int n0, const float* __restrict__ pool1,
                                      const int32_t* __restrict__ idx, const float* __restrict__ x_in, float* __restrict__ y,
                                      long total, int Bt, int B, int HW) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int pix = (int)(i % HW);
@@ -187,6 +199,8 @@ __global__ void gather_images_kernel(const float* __restrict__ pool0, int n0, co
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int HW, int Cp) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over N*HW
     if (i >= total) return;
     long n = i / HW;
@@ -194,6 +208,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
     for (int c = 0; c < Cp; c++) y[i * Cp + c] = c < C ? __ldg(x + (n * C + c) * HW + pix) : 0.f;
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int HW, int Cp) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over N*HW
     if (i >= total) return;
     long n = i / HW;
@@ -205,6 +221,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
 __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict__ out, const float* __restrict__ targets,
                                                         const float* __restrict__ weights, float* __restrict__ sums,
                                                         float* __restrict__ loss, int nseg, int n_per_seg, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[32];
     const int g = blockIdx.x;
     float total = 0.f;
@@ -226,6 +244,8 @@ __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict_
 }
 __global__ void lsgan_bwd_kernel(const float* __restrict__ out, const float* __restrict__ targets, const float* __restrict__ coef,
                                  float* __restrict__ dout, long total, int nseg, int n_per_seg) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int gs = (int)(i / n_per_seg);
@@ -236,6 +256,8 @@ __global__ void lsgan_bwd_kernel(const float* __restrict__ out, const float* __r
 constexpr int FC_PIX = 2048;  // pixels per block
 __global__ void __launch_bounds__(256) focus_fwd_kernel(const float* __restrict__ mask, float* __restrict__ part, int B, int H,
                                                         int W, float center, float eps) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[4 * 32];
     const int g = blockIdx.y;
     const long npix = (long)B * H * W;
@@ -264,6 +286,8 @@ __global__ void __launch_bounds__(256) focus_fwd_kernel(const float* __restrict_
     }
 }
 __global__ void focus_final_kernel(const float* __restrict__ part, float* __restrict__ sums, int G4, int nchunks) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G4) return;
     double s = 0.0;
@@ -273,6 +297,8 @@ __global__ void focus_final_kernel(const float* __restrict__ part, float* __rest
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 __global__ void focus_bwd_kernel(const float* __restrict__ mask, const float* __restrict__ coef, float* __restrict__ dmask,
                                  long total, long npix, int H, int W, float center, float eps) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over G*npix
     if (i >= total) return;
     int g = (int)(i / npix);
@@ -304,6 +330,8 @@ __global__ void focus_bwd_kernel(const float* __restrict__ mask, const float* __
 // ---- Adam: torch.optim.Adam (trainer_council.py:170-179): L2 decay into the gradient, eps 1e-8 ----
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long n, float lr_c1, float b1, float b2, float eps, float wd, float rsq_c2, float gscale) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long stride = (long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -325,56 +353,56 @@ using namespace cg;
 
 extern "C" int cg_mask_head_fwd(const float* h, const float* x_in, float* x_fake, float* mask, int G, int B, int HW, void* stream) {
     long per = (long)B * HW, total = per * G;
-    mask_head_fwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(h, x_in, x_fake, mask, total, per);
+    launch_k(mask_head_fwd_kernel, cdiv(total, 256), 256, 0, ST, h, x_in, x_fake, mask, total, per);
     return check_launch("mask_head_fwd");
 }
 extern "C" int cg_mask_head_bwd(const float* h, const float* x_in, const float* d_xfake, const float* d_mask, float* dh_pre,
                                 int G, int B, int HW, void* stream) {
     long per = (long)B * HW, total = per * G;
-    mask_head_bwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(h, x_in, d_xfake, d_mask, dh_pre, total, per);
+    launch_k(mask_head_bwd_kernel, cdiv(total, 256), 256, 0, ST, h, x_in, d_xfake, d_mask, dh_pre, total, per);
     return check_launch("mask_head_bwd");
 }
 extern "C" int cg_avgpool_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
     CG_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool_fwd: C=%d H=%d W=%d unsupported", C, H, W);
     long total = (long)N * (H / 2) * (W / 2) * (C / 4);
-    avgpool_fwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(x, y, total, H, W, C / 4);
+    launch_k(avgpool_fwd_kernel, cdiv(total, 256), 256, 0, ST, x, y, total, H, W, C / 4);
     return check_launch("avgpool_fwd");
 }
 extern "C" int cg_avgpool_bwd(const float* dy, float* dx, int N, int H, int W, int Cy, int Cx, int nch, int accumulate, void* stream) {
     CG_REQUIRE(nch <= 4 && nch <= Cy && nch <= Cx && H % 2 == 0 && W % 2 == 0, "avgpool_bwd: bad lanes/sizes");
     long total = (long)N * H * W;
-    avgpool_bwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(dy, dx, total, H, W, Cy, Cx, nch, accumulate);
+    launch_k(avgpool_bwd_kernel, cdiv(total, 256), 256, 0, ST, dy, dx, total, H, W, Cy, Cx, nch, accumulate);
     return check_launch("avgpool_bwd");
 }
 extern "C" int cg_acc_slice(float* dst, const float* src, long npix, int Cd, int Cs, int nch, void* stream) {
-    acc_slice_kernel<<<cdiv(npix, 256), 256, 0, ST>>>(dst, src, npix, Cd, Cs, nch);
+    launch_k(acc_slice_kernel, cdiv(npix, 256), 256, 0, ST, dst, src, npix, Cd, Cs, nch);
     return check_launch("acc_slice");
 }
 extern "C" int cg_gather_images(const float* pool0, int n0, const float* pool1, const int32_t* idx, const float* x_in, float* y,
                                 int G, int Bt, int B, int HW, void* stream) {
     long total = (long)G * Bt * HW;
-    gather_images_kernel<<<cdiv(total, 256), 256, 0, ST>>>(pool0, n0, pool1, idx, x_in, y, total, Bt, B, HW);
+    launch_k(gather_images_kernel, cdiv(total, 256), 256, 0, ST, pool0, n0, pool1, idx, x_in, y, total, Bt, B, HW);
     return check_launch("gather_images");
 }
 extern "C" int cg_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int Cp, void* stream) {
     long total = (long)N * HW;
-    nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, ST>>>(x, y, total, C, HW, Cp);
+    launch_k(nchw_to_nhwc_kernel, cdiv(total, 256), 256, 0, ST, x, y, total, C, HW, Cp);
     return check_launch("nchw_to_nhwc");
 }
 extern "C" int cg_nhwc_to_nchw(const float* x, float* y, int N, int C, int HW, int Cp, void* stream) {
     long total = (long)N * HW;
-    nhwc_to_nchw_kernel<<<cdiv(total, 256), 256, 0, ST>>>(x, y, total, C, HW, Cp);
+    launch_k(nhwc_to_nchw_kernel, cdiv(total, 256), 256, 0, ST, x, y, total, C, HW, Cp);
     return check_launch("nhwc_to_nchw");
 }
 extern "C" int cg_lsgan_fwd(const float* out, const float* targets, const float* weights, float* sums, float* loss, int G,
                             int nseg, int n_per_seg, int accumulate, void* stream) {
-    lsgan_fwd_kernel<<<G, 256, 0, ST>>>(out, targets, weights, sums, loss, nseg, n_per_seg, accumulate);
+    launch_k(lsgan_fwd_kernel, G, 256, 0, ST, out, targets, weights, sums, loss, nseg, n_per_seg, accumulate);
     return check_launch("lsgan_fwd");
 }
 extern "C" int cg_lsgan_bwd(const float* out, const float* targets, const float* coef, float* dout, int G, int nseg, int n_per_seg,
                             void* stream) {
     long total = (long)G * nseg * n_per_seg;
-    lsgan_bwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(out, targets, coef, dout, total, nseg, n_per_seg);
+    launch_k(lsgan_bwd_kernel, cdiv(total, 256), 256, 0, ST, out, targets, coef, dout, total, nseg, n_per_seg);
     return check_launch("lsgan_bwd");
 }
 extern "C" int cg_focus_fwd(const float* mask, float* sums, int G, int B, int H, int W, float center, float eps, void* ws,
@@ -386,15 +414,15 @@ extern "C" int cg_focus_fwd(const float* mask, float* sums, int G, int B, int H,
         set_error("focus_fwd: workspace %zu < %zu bytes", ws_bytes, need);
         return CG_ERR_WORKSPACE;
     }
-    focus_fwd_kernel<<<dim3(nchunks, G), 256, 0, ST>>>(mask, (float*)ws, B, H, W, center, eps);
+    launch_k(focus_fwd_kernel, dim3(nchunks, G), 256, 0, ST, mask, (float*)ws, B, H, W, center, eps);
     if (int rc = check_launch("focus_fwd")) return rc;
-    focus_final_kernel<<<cdiv(G * 4, 64), 64, 0, ST>>>((const float*)ws, sums, G * 4, nchunks);
+    launch_k(focus_final_kernel, cdiv(G * 4, 64), 64, 0, ST, (const float*)ws, sums, G * 4, nchunks);
     return check_launch("focus_final");
 }
 extern "C" int cg_focus_bwd(const float* mask, const float* coef, float* dmask, int G, int B, int H, int W, float center,
                             float eps, void* stream) {
     long npix = (long)B * H * W, total = npix * G;
-    focus_bwd_kernel<<<cdiv(total, 256), 256, 0, ST>>>(mask, coef, dmask, total, npix, H, W, center, eps);
+    launch_k(focus_bwd_kernel, cdiv(total, 256), 256, 0, ST, mask, coef, dmask, total, npix, H, W, center, eps);
     return check_launch("focus_bwd");
 }
 extern "C" int cg_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
@@ -403,6 +431,6 @@ extern "C" int cg_adam_step(float* p, const float* g, float* m, float* v, long n
     float lr_c1 = (float)((double)lr / bc1), rsq_c2 = (float)(1.0 / sqrt(bc2));
     int blocks = cdiv(n, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    adam_kernel<<<blocks, 256, 0, ST>>>(p, g, m, v, n, lr_c1, beta1, beta2, eps, weight_decay, rsq_c2, grad_scale);
+    launch_k(adam_kernel, blocks, 256, 0, ST, p, g, m, v, n, lr_c1, beta1, beta2, eps, weight_decay, rsq_c2, grad_scale);
     return check_launch("adam");
 }
