@@ -138,6 +138,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
     g_fwd_2cta = ((mode >> 17) & 1) ? 0 : 1;    // bit 17: one forward / dgrad CTA per SM for tiles <= 64 wide (default: two co-resident)
     g_img_path = ((mode >> 19) & 1) ? 0 : 1;    // bit 19: image-side layers on the older paths (TMA im2col forward, explicit patch matrix weight gradient)
     g_epi_coalesce = ((mode >> 20) & 1) ? 0 : (((mode >> 21) & 1) ? 2 : 1);  // bit 20: accumulator-layout epilogue stores everywhere; bit 21: the coalescing patch on the wide tiles too
+    g_small_bn = ((mode >> 23) & 1) ? 0 : 1;  // bit 23: keep the widest N tile even when the launch has fewer tiles than SMs
     g_pdl = ((mode >> 22) & 1) ? 0 : 1;  // bit 22: plain stream-serialised launches
     g_pair_cap = (mode >> 8) & 0xff;  // bits 8..15: cap on the number of CTA pairs launched (0 = as many as are co-resident)
     return prev;

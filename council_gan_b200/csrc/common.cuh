@@ -20,6 +20,7 @@ extern thread_local int g_wgrad_xm;
 extern thread_local int g_wgrad_2cta;
 extern thread_local int g_fwd_2cta;
 extern thread_local int g_epi_coalesce;
+extern thread_local int g_small_bn;
 extern thread_local int g_wgrad_xm2;
 
 constexpr int CG_MAX_DEVICES = 64;

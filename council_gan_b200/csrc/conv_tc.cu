@@ -58,6 +58,7 @@ thread_local int g_pair_cap = 0;
 thread_local int g_wgrad_xm = 1;  // x-on-M weight gradient for <= 64 output channels
 thread_local int g_wgrad_2cta = 1;  // two co-resident weight-gradient CTAs per SM (run 44: -14..-33 % on the >= 128-channel layers)
 thread_local int g_wgrad_xm2 = 1;   // ... also for the x-on-M kernel
+thread_local int g_small_bn = 1;  // narrower N tiles when a launch has fewer tiles than SMs (mode bit 23 clears it)
 thread_local int g_epi_coalesce = 1;  // epilogue stores through the per-warp patch (full sectors); bit 20 of the mode clears it
 thread_local int g_fwd_2cta = 1;    // two co-resident forward / data-gradient CTAs per SM for tiles <= 64 channels wide (run 46: -1.4 ms/step)
 thread_local int g_pair_mode = 3;  // bit 0: 256-wide tiles, bit 1: 128-wide, bit 2: 64-wide (measured slower than single CTAs: off),
@@ -886,6 +887,16 @@ static int pick_bk(int cin) {
     return 0;
 }
 
+// Few-tile launches (small maps: the 32x32 bottleneck of the 128x128 configuration is 8 pixel tiles per member): narrower N tiles put more
+// SMs to work.  Every extra N tile re-reads the same activation tile, from L2, which is cheap at these sizes; a 3x3 256->256 layer on
+// 1024 pixels x 2 members goes from 8 CTA pairs running 288 K-steps of 256-wide MMAs to 64 CTAs running the same steps 64 wide.
+static int fill_bn(int bn, long mpix, int groups_classes, int cout) {
+    if (!g_small_bn) return bn;
+    const int sms = sm_count_now();
+    while (bn > 64 && cout % (bn / 2) == 0 && (long)groups_classes * cdiv(mpix, TC_BM) * (cout / bn) < sms) bn >>= 1;
+    return bn;
+}
+
 bool tc_fwd_supported(const cg_conv_geom& g) {
     init_driver();
     if (!g_encode_tiled || !g_encode_im2col) return false;
@@ -1030,6 +1041,7 @@ int tc_conv_fwd(const cg_conv_geom& g, const float* x, const float* w, const flo
     p.stats = stats_part;
     p.stats_gbc = (long)g.G * g.B * g.Cout;
     p.bn = pick_bn(g.Cout);
+    if (p.bn > 64) p.bn = fill_bn(p.bn, (long)g.B * (g.ups ? g.H * g.W : g.Ho * g.Wo), g.G * (g.ups ? 4 : 1), g.Cout);
     p.n_store = p.bn == 16 ? g.Cout : p.bn;
     p.bk = pick_bk(g.Cin);
     long nimg = (long)(g.x_groups == 1 ? 1 : g.G) * g.B;
@@ -1158,6 +1170,7 @@ int tc_conv_dgrad(const cg_conv_geom& g, const float* dy, const float* w, float*
 
     TcParams p{};
     p.bn = pick_bn(g.Cin);
+    if (p.bn > 64) p.bn = fill_bn(p.bn, (long)g.B * ((g.ups ? 2 * g.H : g.H) / g.stride) * ((g.ups ? 2 * g.W : g.W) / g.stride), g.G * g.stride * g.stride, g.Cin);
     p.n_store = p.bn == 16 ? g.Cin : p.bn;
     p.bk = pick_bk(g.Cout);
     long ktot = (long)TH * TW * g.Cout;
