@@ -1834,6 +1834,17 @@ static void wg_plan(const cg_conv_geom& g, int& splits, long& chunk) {
         double score = eff - 0.01 * s - (waves < 3 ? 0.15 * (3 - waves) : 0.0);
         if (score > best_score) { best_score = score; best = s; }
     }
+    // Small problems (few output tiles, e.g. a 1x1 64->64 layer: 2 units per member): the score above never leaves one split because
+    // each extra split fills < 1 % of a wave, and two CTAs then walk all the pixels (0.15 ms for 134 MFLOP at 128x128).  Below half a
+    // wave, take as many splits as fill one wave (each still >= 8 pipeline stages), capped so the partial sums stay <= 32 MB.
+    if (g_small_bn && base * best * 2 < sms) {
+        long fill = sms / base;
+        const long out_bytes = (long)g.G * g.Cout * g.KH * g.KW * g.Cin * 4;
+        const long cap = (32l << 20) / (out_bytes > 0 ? out_bytes : 1);
+        if (fill > cap) fill = cap;
+        if (fill > maxs) fill = maxs;
+        if (fill > best) best = (int)fill;
+    }
     splits = best;
     chunk = ((Mpix + splits - 1) / splits + kp - 1) / kp * kp;
     splits = (int)((Mpix + chunk - 1) / chunk);
