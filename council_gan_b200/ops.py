@@ -145,10 +145,20 @@ class CudaOps:
         # the main stream.  bank.grad is written only by conv_wgrad and read only after wgrad_join() (trainer _adam).
         self._wgrad_stream = torch.cuda.Stream(self.device) if os.environ.get('COUNCIL_WGRAD_STREAM', '0') == '1' else None
         self._ws_side = None
+        self._stream_cached = None
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        c = self._stream_cached
+        return c if c is not None else torch.cuda.current_stream(self.device).cuda_stream
+
+    def pin_stream(self):
+        """Resolve torch's current stream ONCE for a run of launches (the trainer pins it for the duration of an update: the lookup
+        was 19 % of the host time of a step on the launch-bound 128x128 configuration, profiles/r02_runM_host_profile_glasses.txt)."""
+        self._stream_cached = torch.cuda.current_stream(self.device).cuda_stream
+
+    def unpin_stream(self):
+        self._stream_cached = None
 
     def _ck(self, rc, what):
         if rc != 0:

@@ -30,6 +30,7 @@ nsgan/RaHinge, do_my_style, gray-scale D, random D/G pairing) raise NotImplement
 from __future__ import annotations
 
 import math
+import functools
 import os
 import random
 from collections import deque
@@ -49,6 +50,21 @@ def _dist():
     if dist.is_available() and dist.is_initialized():
         return dist
     return None
+
+
+def _pinned(fn):
+    """Run an update with the launch stream resolved once (ops.pin_stream) instead of once per kernel."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        ops = self.ops
+        if not hasattr(ops, 'pin_stream') or ops._stream_cached is not None:
+            return fn(self, *args, **kwargs)
+        ops.pin_stream()
+        try:
+            return fn(self, *args, **kwargs)
+        finally:
+            ops.unpin_stream()
+    return wrapper
 
 
 class Council_Trainer(nn.Module):
@@ -356,6 +372,7 @@ class Council_Trainer(nn.Module):
     # ==================================================================================================
     # dis_update   (trainer_council.py:735-780)
     # ==================================================================================================
+    @_pinned
     def dis_update(self, x_a=None, x_b=None, hyperparameters=None):
         hp = hyperparameters
         self._check_supported(hp)
@@ -396,6 +413,7 @@ class Council_Trainer(nn.Module):
     # ==================================================================================================
     # dis_council_update   (trainer_council.py:782-883)
     # ==================================================================================================
+    @_pinned
     def dis_council_update(self, x_a=None, x_b=None, hyperparameters=None):
         hp = hyperparameters
         cc = hp['council']
@@ -478,6 +496,7 @@ class Council_Trainer(nn.Module):
     # ==================================================================================================
     # gen_update   (trainer_council.py:280-634)
     # ==================================================================================================
+    @_pinned
     def gen_update(self, x_a, x_b, hyperparameters, iterations=0):
         hp = hyperparameters
         self.hyperparameters = hp
@@ -610,6 +629,7 @@ class Council_Trainer(nn.Module):
                 continue
             self._sched_epoch[fam] += 1
 
+    @_pinned
     def sample(self, x_a=None, x_b=None, s_a=None, s_b=None, council_member_to_sample_vec=None, return_mask=True):
         """Translation of every image by every member (:643-733): returns the same 8-tuple, rows ordered image-major /
         member-minor like the reference's double loop.  All members and all images run as ONE stacked pass per network
