@@ -124,6 +124,7 @@ class CudaOps:
         if not torch.cuda.is_available():
             raise RuntimeError('council_gan_b200 needs a CUDA device (sm_100a); no CPU path exists')
         self.lib = load_library()
+        self._stream_cached = None
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
