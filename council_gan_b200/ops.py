@@ -202,9 +202,22 @@ class CudaOps:
 
     _tc_mode = 1
 
+    pdl = False
+
     def set_tensor_core_mode(self, mode):
-        self._tc_mode = int(mode)
-        return self.lib.cg_set_tensor_core_mode(int(mode))
+        """mode as cg_set_tensor_core_mode documents it; the programmatic-dependent-launch bit (1 << 22) is added here when set_pdl(True)"""
+        self._tc_mode = mode = int(mode)
+        eff = 7 if mode == 1 else mode
+        if self.pdl and mode:
+            eff |= 1 << 22
+        return self.lib.cg_set_tensor_core_mode(eff)
+
+    def set_pdl(self, on):
+        """Programmatic dependent launch between the library's kernels: pays on launch-bound small maps, costs ~2 % on long kernels."""
+        on = bool(on)
+        if on != self.pdl:
+            self.pdl = on
+            self.set_tensor_core_mode(self._tc_mode)
 
     # -- live per-kernel timing (bench.py roofline): CUDA events on the launching stream ----------
     _timing = None

@@ -52,6 +52,10 @@ def _dist():
     return None
 
 
+_PDL = os.environ.get('COUNCIL_PDL', 'auto')   # auto | 0 | 1
+_PDL_MAX_PIXELS = 128 * 128 * 4             # batch x height x width up to which programmatic dependent launch is switched on
+
+
 def _pinned(fn):
     """Run an update with the launch stream resolved once (ops.pin_stream) instead of once per kernel."""
     @functools.wraps(fn)
@@ -60,6 +64,14 @@ def _pinned(fn):
         if not hasattr(ops, 'pin_stream') or ops._stream_cached is not None:
             return fn(self, *args, **kwargs)
         ops.pin_stream()
+        if _PDL != 'auto':
+            ops.set_pdl(_PDL == '1')
+        else:  # launch-bound small maps only (measured: -4 % at 128x128 x 1, +2 % at 256x256 x 8)
+            for x in args:
+                if torch.is_tensor(x):
+                    pix = x.numel() // (IMG_C if x.dim() == 5 else max(int(x.shape[1]), 1)) if x.dim() >= 4 else 0
+                    ops.set_pdl(0 < pix <= _PDL_MAX_PIXELS)
+                    break
         try:
             return fn(self, *args, **kwargs)
         finally:

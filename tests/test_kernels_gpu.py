@@ -89,13 +89,13 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64 | (1 << 16), 7 | (1 << 17), 7 | (1 << 19), 7 | (1 << 20), 7 | (1 << 21), 7 | (1 << 23)])
+@pytest.mark.parametrize('tc', [0, 1, 7 | 32 | 64 | (1 << 16), 7 | (1 << 17), 7 | (1 << 19), 7 | (1 << 20), 7 | (1 << 21), 7 | (1 << 22), 7 | (1 << 23)])
 def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
     """tc = 0: SIMT fp32; 1: the default tensor-core dispatch; 7|32|64|1<<16: the switchable variants that are off by default --
     CTA pairs (cta_group::2) for 64-wide forward tiles and in the weight gradient, one weight-gradient CTA per SM instead of the default two;
     7|1<<17: ONE forward / data-gradient CTA per SM for tiles <= 64 channels wide (the default co-schedules two);
     7|1<<20: accumulator-layout epilogue stores everywhere (the default sends tiles <= 64 channels wide through the coalescing
-    shared-memory patch); 7|1<<21: the patch on the wide tiles too; 7|1<<23: widest N tile even on small maps (the default narrows
+    shared-memory patch); 7|1<<21: the patch on the wide tiles too; 7|1<<22: programmatic dependent launch; 7|1<<23: widest N tile even on small maps (the default narrows
     the tile when a launch has fewer tiles than SMs -- which these test shapes do, so tc=1 exercises the narrowed tiles and this one the wide)."""
     name, G, Gx, B, H, W, Cin, Cout, K, stride, pad, ups = case
     if tc == 7 | (1 << 19):
@@ -103,7 +103,7 @@ def test_conv_fwd_dgrad_wgrad(ops, ref, case, tc):
         # TMA-im2col forward / explicit-patch weight gradient, which stay tested
         if not (Cin <= 8 and Cout == 64 and K * K * Cin <= 96):
             pytest.skip('not an image-side layer')
-    elif tc in (7 | (1 << 20), 7 | (1 << 21), 7 | (1 << 23)):
+    elif tc in (7 | (1 << 20), 7 | (1 << 21), 7 | (1 << 22), 7 | (1 << 23)):
         if not name.startswith('tc_'):
             pytest.skip('not a tensor-core forward / data-gradient geometry')
     elif tc > 1 and not (name.startswith('tc_') and (Cout % 128 == 0 or Cout <= 64 or Cin <= 64)):
