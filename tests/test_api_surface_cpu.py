@@ -199,3 +199,53 @@ def test_weight_init_statistics():
         assert all(float(v.abs().max()) == 0 for k, v in sdd.items() if k.endswith('.bias'))
     a, b = tr2.gen_a2b_s[0].state_dict(), tr2.gen_a2b_s[1].state_dict()
     assert not torch.equal(a['dec.model.2.conv.weight'], b['dec.model.2.conv.weight'])  # members are initialised independently
+
+
+def test_update_pins_the_stream_and_picks_pdl_by_batch_size():
+    """host logic of the launch path: an update resolves the stream once (ops.pin_stream / unpin_stream around the call, also when it
+    raises) and turns programmatic dependent launch on only for small batches (COUNCIL_PDL=auto)."""
+    from council_gan_b200 import trainer_council as tc
+
+    class FakeOps:
+        def __init__(self):
+            self._stream_cached, self.log = None, []
+
+        def pin_stream(self):
+            self._stream_cached = 1
+            self.log.append('pin')
+
+        def unpin_stream(self):
+            self._stream_cached = None
+            self.log.append('unpin')
+
+        def set_pdl(self, on):
+            self.log.append(('pdl', bool(on)))
+
+    class T:
+        def __init__(self):
+            self.ops = FakeOps()
+
+        @tc._pinned
+        def update(self, x, fail=False):
+            assert self.ops._stream_cached == 1
+            if fail:
+                raise ValueError('boom')
+            return self.nested(x)
+
+        @tc._pinned
+        def nested(self, x):  # an update called from inside another one does not unpin
+            return 'ok'
+
+    t = T()
+    assert t.update(torch.zeros(1, 3, 128, 128)) == 'ok'
+    assert t.ops.log == ['pin', ('pdl', True), 'unpin'] and t.ops._stream_cached is None
+    t.ops.log.clear()
+    t.update(torch.zeros(8, 3, 256, 256))
+    assert t.ops.log == ['pin', ('pdl', False), 'unpin']
+    t.ops.log.clear()
+    t.update(torch.zeros(1, 2, 64, 64, tc.IMG_C))  # channels-last device batch [1, B, H, W, lanes]
+    assert t.ops.log[1] == ('pdl', True)
+    t.ops.log.clear()
+    with pytest.raises(ValueError):
+        t.update(torch.zeros(1, 3, 64, 64), fail=True)
+    assert t.ops.log[-1] == 'unpin' and t.ops._stream_cached is None
