@@ -234,3 +234,20 @@ class DeviceFolderLoader:
             else:
                 nxt = None
             yield self.aug([f.result() for f in cur], want_nchw=self.want_nchw)
+
+
+def get_all_data_loaders(ops, conf, want_nchw=False):
+    """``utils.get_all_data_loaders(conf)`` (utils.py:45-104) for the folder layout the shipped configs use
+    (``data_root``/{trainA,trainB,testA,testB}): -> (train_loader_a, train_loader_b, test_loader_a, test_loader_b), each a one-element
+    list like the reference's.  Train loaders crop to crop_image_height x crop_image_width, test loaders to new_size x new_size."""
+    if 'data_root' not in conf:
+        raise NotImplementedError('list-file datasets (data_folder_train_a / data_list_train_a) are not on the device-side input pipeline')
+    if conf.get('inbalenceDataSets', {}).get('imbalance_sub_dataset', False):
+        raise NotImplementedError('imbalanced sub-dataset sampling (inbalenceDataSets) is not on the device-side input pipeline')
+    if conf.get('input_dim_a', 3) == 1 or conf.get('input_dim_b', 3) == 1:
+        raise NotImplementedError('single-channel domains (dim3to1) are not on the device-side input pipeline')
+    bs, nw, root = conf['batch_size'], conf.get('num_workers', 4), conf['data_root']
+
+    def mk(sub, train, is_a):
+        return [DeviceFolderLoader(ops, os.path.join(root, sub), bs, train, conf, is_a, num_workers=nw, want_nchw=want_nchw)]
+    return mk('trainA', True, True), mk('trainB', True, False), mk('testA', False, True), mk('testB', False, False)

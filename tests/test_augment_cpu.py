@@ -134,6 +134,21 @@ def test_trainer_takes_the_device_batches_as_they_are(tmp_path):
         for k in range(4):
             PIL.fromarray(rnd_img(rng, 80, 72, True)).save(str(tmp_path / dom / ('%d.png' % k)))
     ops = TorchOps('cpu')
+    # utils.get_all_data_loaders(conf): four one-element lists; test loaders crop to new_size and neither shuffle nor augment
+    from council_gan_b200.data import get_all_data_loaders
+    for dom in ('testA', 'testB'):
+        (tmp_path / dom).mkdir()
+        PIL.fromarray(rnd_img(rng, 80, 72, True)).save(str(tmp_path / dom / '0.png'))
+    conf = dict(hp, data_root=str(tmp_path), batch_size=1, num_workers=1)
+    tra, trb, tea, teb = get_all_data_loaders(ops, conf)
+    assert [len(v) for v in (tra, trb, tea, teb)] == [1, 1, 1, 1] and len(tra[0]) == 4 and len(tea[0]) == 1
+    torch.manual_seed(0)
+    t1 = next(iter(tea[0]))
+    torch.manual_seed(0)
+    t2 = next(iter(tea[0]))   # the reference's test stack still draws a RandomCrop window (71 x 64 -> 64 x 64 here): same seed, same batch
+    assert t1.shape == (1, 1, 64, 64, 4) and torch.equal(t1, t2)
+    with pytest.raises(NotImplementedError):
+        get_all_data_loaders(ops, dict(conf, inbalenceDataSets={'imbalance_sub_dataset': True}))
     losses = []
     for want_nchw in (False, True):
         torch.manual_seed(3)
