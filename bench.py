@@ -11,7 +11,7 @@ Default workload = BASELINE.json configs[1]: male2female 256x256, council_size=4
 Prints ONE JSON line (rank 0).  `value` = images/sec with inputs resident in HBM; `e2e` = the same through
 the public Council_Trainer API with HOST (pinned) image tensors: H2D copies and the D2H loss read are inside
 the timed region.  `roofline` is for the dominant convolution kernel, timed live with CUDA events on the
-launching stream.
+launching stream in a second timed region of the same K steps (the headline region carries no per-kernel events).
 
 Comparison legs (measurement infrastructure, baseline/ref_runner.py):
   * `cpu_baseline` / `--impl reference`: the UNMODIFIED reference (`$COUNCIL_REF_DIR` -> /root/reference -> baseline/_ref; else the
