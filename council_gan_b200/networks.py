@@ -244,7 +244,9 @@ class CouncilGen(_StackedNet):
         self.fuse_stats = os.environ.get('COUNCIL_FUSE_STATS', 'auto')
         # single-launch normalisation with L2-resident second pass (csrc/norm_coop.cu): correct and tested, but measured equal to the
         # two- / three-kernel forms inside the step (profiles/r02_runB_*), so it is opt-in: COUNCIL_COOP_NORM=1
-        self.coop_norm = os.environ.get('COUNCIL_COOP_NORM', '0') == '1'
+        coop = os.environ.get('COUNCIL_COOP_NORM', '0')  # 0 | 1 (forward and backward) | bwd (backward only: keeps the statistics epilogue)
+        self.coop_norm = coop == '1'
+        self.coop_norm_bwd = coop in ('1', 'bwd')
         self.fuse_head = os.environ.get('COUNCIL_FUSE_HEAD', '1') == '1'  # decoder tail of no-grad passes as one kernel (csrc/head_fused.cu)
         self.dim, self.style_dim, self.nd, self.nr, self.mlp_dim = g['dim'], g['style_dim'], g['n_downsample'], g['n_res'], g['mlp_dim']
         dim, nd, nr = self.dim, self.nd, self.nr
@@ -381,7 +383,7 @@ class CouncilGen(_StackedNet):
         ops = self.ops
         x, y, mean, rstd = rec
         off = self.adain_off.get(s.key, 0)
-        norm_bwd = ops.norm_fused_bwd if self.coop_norm else ops.norm_act_bwd
+        norm_bwd = ops.norm_fused_bwd if self.coop_norm_bwd else ops.norm_act_bwd
         dy = norm_bwd(dz, y, mean, rstd, adain, off, act, ups_out, d_adain)
         ops.conv_wgrad(x, dy, self.bank.g(s.wname), None, s.stride, s.pad)
         if not need_dx:
