@@ -139,7 +139,7 @@ extern "C" int cg_set_tensor_core_mode(int mode) {
     g_img_path = ((mode >> 19) & 1) ? 0 : 1;    // bit 19: image-side layers on the older paths (TMA im2col forward, explicit patch matrix weight gradient)
     g_epi_coalesce = ((mode >> 20) & 1) ? 0 : (((mode >> 21) & 1) ? 2 : 1);  // bit 20: accumulator-layout epilogue stores everywhere; bit 21: the coalescing patch on the wide tiles too
     g_small_bn = ((mode >> 23) & 1) ? 0 : 1;  // bit 23: keep the widest N tile even when the launch has fewer tiles than SMs
-    g_pdl = ((mode >> 22) & 1) ? 1 : 0;  // bit 22: programmatic dependent launch (wins on launch-bound small maps, loses ~2 % at 256x256 x 8)
+    g_pdl = ((mode >> 22) & 1) ? 1 : (((mode >> 24) & 1) ? 2 : 0);  // bit 24: PDL for the helper kernels only  // bit 22: programmatic dependent launch (wins on launch-bound small maps, loses ~2 % at 256x256 x 8)
     g_pair_cap = (mode >> 8) & 0xff;  // bits 8..15: cap on the number of CTA pairs launched (0 = as many as are co-resident)
     return prev;
 }

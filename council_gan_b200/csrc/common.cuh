@@ -79,7 +79,8 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    // g_pdl: 0 off, 1 every kernel, 2 only the helper kernels (no dynamic shared memory: transforms, finalisers, reductions, pointwise passes)
+    at[0].val.programmaticStreamSerializationAllowed = (g_pdl == 1 || (g_pdl == 2 && smem == 0)) ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through check_launch()'s cudaGetLastError

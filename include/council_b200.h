@@ -64,6 +64,7 @@ int cg_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * stores instead of the coalescing shared-memory patch (default: patch for tiles <= 64 channels wide; 1<<21 = for the wide tiles too),
  * 1<<22 = programmatic dependent launch between this library's kernels (every kernel carries the griddepcontrol pair; measured -4 % on the
  * launch-bound 128x128 configuration and +2 % at 256x256 batch 8, so the trainer turns it on for small maps only),
+ * 1<<24 = programmatic dependent launch for the helper kernels only (those without dynamic shared memory),
  * 1<<23 = keep the widest N tile on small maps (default: narrower tiles when a launch has fewer tiles than SMs), bits 8..15 = cap on the CTA pairs launched.
  * The switches are per calling thread (like cg_last_error), not process-global.  Returns the previous mask. */
 int cg_set_tensor_core_mode(int mode);
